@@ -1,0 +1,189 @@
+"""Generate golden vectors by running the UNMODIFIED reference in this container.
+
+TEST INFRASTRUCTURE.  Run here (CPU, /root/reference present):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference cannot travel to the GPU box, so its outputs are committed as small
+fixtures.  How the reference is driven:
+  * ``gmm_model.py`` / ``model_v2.py`` import cleanly and are used as-is;
+  * the trainers execute training at import and need absent packages, so the step
+    functions (``std_normal, loss_function, latent_regularized_loss_function, train,
+    evaluate, convert_to_one_hot``) are AST-extracted and exec'd in a namespace holding
+    ``model, optimizer, args, step``;
+  * CPU only: hard-coded ``.cuda()`` calls are neutralised with
+    ``torch.Tensor.cuda = identity``.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("FADER_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+sys.path.insert(0, os.path.dirname(HERE))
+
+STEP_FUNCS = ("std_normal", "loss_function", "latent_regularized_loss_function", "train",
+              "evaluate", "convert_to_one_hot")
+
+
+def load_reference():
+    """Returns (gmm_model module, model_v2 module)."""
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self          # shim 2 (CPU only)
+    sys.path.insert(0, REF)
+    import gmm_model
+    import model_v2
+    return gmm_model, model_v2
+
+
+def extract_step_functions(trainer_file: str, namespace: dict) -> dict:
+    """AST-extract the step functions of a trainer script into ``namespace``."""
+    src = open(os.path.join(REF, trainer_file)).read()
+    tree = ast.parse(src)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in STEP_FUNCS]
+    mod = ast.Module(body=body, type_ignores=[])
+    exec(compile(mod, trainer_file, "exec"), namespace)
+    return namespace
+
+
+def trainer_namespace(model, optimizer, args, step=0):
+    from torch import nn, optim
+    from torch.distributions import Normal, kl_divergence
+    from torch.nn import functional as F
+    return dict(model=model, optimizer=optimizer, args=args, step=step, np=np, torch=torch,
+                F=F, nn=nn, optim=optim, Normal=Normal, kl_divergence=kl_divergence)
+
+
+def make_case(variant: str, H: int, Z: int, K: int, B: int, T: int, seed: int):
+    from oracle import fader_oracle as fo
+    gmm_model, model_v2 = load_reference()
+    torch.manual_seed(seed)
+    if variant == "gmvae":
+        model = gmm_model.MusicAttrRegGMVAE(342, 3, 16, 24, H, Z, 32, n_component=K)
+        trainer = "trainer_gmm.py"
+    else:
+        model = model_v2.MusicAttrRegVAE(342, 3, 16, 24, H, Z, 32)
+        trainer = "trainer.py"
+    model.train()
+    args = dict(lr=1e-3, beta=0.2)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args["lr"])
+    ns = extract_step_functions(trainer, trainer_namespace(model, optimizer, args))
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    d, r, n, c, r_density, n_density = fo.synth_batch(B, T, seed=seed + 1, pad_tail=True)
+    d_oh, r_oh, n_oh = (ns["convert_to_one_hot"](x, dims) for x, dims in ((d, 342), (r, 3), (n, 16)))
+    y_label = torch.randint(0, max(K, 1), (B,), generator=torch.Generator().manual_seed(seed + 2))
+    g = {"B": B, "T": T, "H": H, "Z": Z, "K": K, "d": d.numpy(), "r": r.numpy(), "n": n.numpy(),
+         "c": c.numpy(), "r_density": r_density, "n_density": n_density, "y_label": y_label.numpy()}
+    for k, v in sd0.items():
+        g["w/" + k] = v.numpy()
+
+    # ---- (1) one forward + every loss variant + gradients, noise replayed ----------
+    STEP = 20000
+    torch.manual_seed(seed + 3)
+    eps_r, eps_n = fo.draw_eps(B, Z, T)
+    g["eps_r"], g["eps_n"] = eps_r.numpy(), eps_n.numpy()
+    torch.manual_seed(seed + 3)
+    res = model(d_oh, r_oh, n_oh, c)
+    if variant == "gmvae":
+        output, dis, z_out, logLogit_out, qy_x_out, y_out = res
+        out, r_out, n_out = output[:3]
+        for a, i in (("r", 0), ("n", 1)):
+            g[f"logLogit_{a}"] = logLogit_out[i].detach().numpy()
+            g[f"qy_x_{a}"] = qy_x_out[i].detach().numpy()
+            g[f"y_{a}"] = y_out[i].numpy()
+        terms = ns["loss_function"](out, d, r_out, r, n_out, n, dis, qy_x_out, logLogit_out, STEP, beta=0.2)
+        names = ("loss", "CE_X", "CE_R", "CE_N", "kld_lat_r", "kld_lat_n", "kld_cls_r", "kld_cls_n")
+    else:
+        output, dis, z_out = res
+        out, r_out, n_out = output
+        ns["step"] = STEP                                     # trainer.py reads the module global
+        terms = ns["loss_function"](out, d, r_out, r, n_out, n, dis, beta=0.2)
+        names = ("loss", "CE_X", "CE_R", "CE_N")
+    l_r, l_n = ns["latent_regularized_loss_function"](z_out, r_density, n_density)
+    total = terms[0] + l_r + l_n
+    optimizer.zero_grad()
+    total.backward()
+    for nm, t in zip(names, terms):
+        g["loss/" + nm] = np.float64(t.detach().reshape(-1)[0].item())
+    g["loss/l_r"], g["loss/l_n"] = np.float64(l_r.item()), np.float64(l_n.item())
+    g["loss/total"] = np.float64(total.detach().reshape(-1)[0].item())
+    g["out"], g["r_out"], g["n_out"] = out.detach().numpy(), r_out.detach().numpy(), n_out.detach().numpy()
+    for a, i in (("r", 0), ("n", 1)):
+        g[f"mu_{a}"], g[f"scale_{a}"] = dis[i].mean.detach().numpy(), dis[i].stddev.detach().numpy()
+        g[f"z_{a}"] = z_out[i].detach().numpy()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            g["grad/" + k] = p.grad.detach().clone().numpy()
+    g["live"] = np.array(sorted(k for k, p in model.named_parameters() if p.grad is not None))
+
+    # ---- (2) other loss branches on the same forward --------------------------------
+    if variant == "gmvae":
+        with torch.no_grad():
+            for tag, st in (("neg_beta", 5000), ("zero_beta", 10)):
+                t2 = ns["loss_function"](out, d, r_out, r, n_out, n, dis, qy_x_out, logLogit_out, st, beta=0.2)
+                g[f"loss_{tag}/loss"] = np.float64(t2[0].reshape(-1)[0].item())
+        # supervised branch incl. its gradients (fresh forward, same noise)
+        torch.manual_seed(seed + 3)
+        res = model(d_oh, r_oh, n_oh, c)
+        output, dis, z_out, logLogit_out, qy_x_out, y_out = res
+        t3 = ns["loss_function"](output[0], d, output[1], r, output[2], n, dis, qy_x_out, logLogit_out,
+                                 STEP, beta=0.2, is_supervised=True, y_label=y_label)
+        l_r, l_n = ns["latent_regularized_loss_function"](z_out, r_density, n_density)
+        optimizer.zero_grad()
+        (t3[0] + l_r + l_n).backward()
+        g["loss_sup/loss"] = np.float64(t3[0].detach().reshape(-1)[0].item())
+        g["loss_sup/kld_lat_r"] = np.float64(t3[4].item())
+        g["loss_sup/kld_lat_n"] = np.float64(t3[5].item())
+        for k in ("mu_r.weight", "mu_r_lookup.weight", "gru_n.weight_hh_l0_reverse", "grucell_g.weight_ih"):
+            g["grad_sup/" + k] = dict(model.named_parameters())[k].grad.detach().clone().numpy()
+
+    # ---- (3) two full train() calls from the initial weights -----------------------
+    model.load_state_dict(sd0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args["lr"])
+    ns["optimizer"] = optimizer
+    torch.manual_seed(seed + 4)
+    traj = []
+    step = STEP
+    for it in range(2):
+        if variant == "gmvae":
+            step, o = ns["train"](step, d_oh, r_oh, n_oh, d, r, n, c, r_density, n_density)
+        else:
+            ns["step"] = step
+            step, o = ns["train"](step, d_oh, r_oh, n_oh, d, r, n, c, r_density, n_density)
+        traj.append(o)
+    g["train/outputs"] = np.array(traj, dtype=np.float64)
+    for k, p in model.named_parameters():
+        if ("grad/" + k) in g:
+            g["w2/" + k] = p.detach().clone().numpy()
+
+    # ---- (4) eval-mode greedy decode (test_class.py:250-253; notebook cell 15) ------
+    model.load_state_dict(sd0)
+    model.eval()
+    with torch.no_grad():
+        zc = torch.cat([torch.from_numpy(g["z_r"]), torch.from_numpy(g["z_n"]), c], 1)
+        dec = model.global_decoder(zc, steps=T + 4)
+    g["decode/logp"] = dec.numpy()
+    g["decode/tokens"] = dec.argmax(-1).numpy()
+    model.train()
+    return g
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for variant, H, Z, K, B, T, seed in (("gmvae", 16, 8, 2, 3, 12, 10), ("vae", 16, 8, 0, 4, 10, 20),
+                                          ("gmvae", 32, 16, 3, 2, 9, 30)):
+        g = make_case(variant, H, Z, K, B, T, seed)
+        path = os.path.join(OUT, f"{variant}_H{H}_Z{Z}_B{B}_T{T}.npz")
+        np.savez_compressed(path, **g)
+        print(path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: float(v) for k, v in g.items() if k.startswith("loss/")})
+
+
+if __name__ == "__main__":
+    main()
