@@ -1,0 +1,231 @@
+/*
+ * fadernets_b200 -- C ABI of the B200 (sm_100a) GM-VAE / VAE hot path.
+ *
+ * The reference (gudgud96/music-fader-nets) has NO native / FFI interface: the path lives in
+ * Python objects.  This header is therefore the boundary a maintainer
+ * would bind from the reference's own files -- every entry point cites the reference lines
+ * (paths relative to the reference checkout) whose arithmetic it replaces.  INTEGRATION.md
+ * shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory unless marked "host";
+ *   - the CALLER owns every buffer (including scratch); the library allocates nothing that
+ *     outlives a call and keeps no mutable global state besides cached device attributes;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host;
+ *   - return value: 0 = OK, negative = FN_ERR_*; fn_last_error() gives the message;
+ *   - activations inside the path are TIME-MAJOR: [T][B][...]; API-facing tensors keep the
+ *     reference's batch-major layout ([B][T][...]) and are converted by the kernels that
+ *     produce / consume them;
+ *   - GRU gate order is PyTorch's (r, z, n); weights keep the reference's state_dict layout.
+ */
+#ifndef FADERNETS_B200_H
+#define FADERNETS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FN_OK 0
+#define FN_ERR_ARG (-1)      /* bad argument / unsupported shape */
+#define FN_ERR_CUDA (-2)     /* a CUDA runtime call failed        */
+#define FN_ERR_UNSUPPORTED (-3)
+
+#define FN_ABI_VERSION 1
+
+const char* fn_last_error(void);
+int fn_abi_version(void);
+/* sm count / compute capability of the current device (host out-params). */
+int fn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense fp32 GEMM with arbitrary operand strides (SIMT FMA path -- exact fp32 parity mode).
+ *   C[m,n] (ldc) = (accumulate ? C[m,n] : 0) + sum_k A(m,k) * B(k,n) + (bias ? bias[n] : 0)
+ *   A(m,k) = A[m*sam + k*sak],  B(k,n) = B[k*sbk + n*sbn];  one of each stride pair must be 1.
+ * Replaces every nn.Linear / addmm on the path: gmm_model.py:86,91 (latent heads), :107,:112
+ * (linear_init_*), :110,:115 (linear_out_r/n), :124 (linear_init_global), :137 (linear_out_g),
+ * the W_ih * x products inside nn.GRU / nn.GRUCell (:33-56) and their autograd transposes.
+ * ---------------------------------------------------------------------------------------- */
+int fn_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
+                float* C, long long ldc, const float* bias, int M, int N, int K, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Persistent time-loop GRU ("gate block": recurrent GEMM + sigma/tanh/Hadamard per step).
+ * One launch runs `n_chains` independent recurrences; each chain is split over hidden-unit
+ * slices (one CTA per slice, W_hh slice resident in shared memory for all T steps) with a
+ * per-chain step barrier in `barrier_ws` (>= 64 * n_chains bytes, zeroed by the call).
+ *
+ * Step s processes time tau = reverse ? T-1-s : s:
+ *   gi = emb[ids[tau][b]] + proj[b] + dense[tau][b]        (each term optional)
+ *   gh = h_prev W_hh^T + b_hh
+ *   r = sigma(gi_r+gh_r); z = sigma(gi_z+gh_z); n = tanh(gi_n + r*gh_n); h = (1-z)*n + z*h_prev
+ * (torch nn.GRU / nn.GRUCell semantics; reference call sites gmm_model.py:84,89 (encoders),
+ *  :109,:114 (sub-decoders), :133,:136 (global decoder cells, teacher-forced: layer 1 consumes
+ *  the token gather, layer 2 consumes `dense` = hx0 W_ih2^T + b_ih2).)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct FnGruChain {
+    /* parameters */
+    const float* w_hh;        /* [3H][H]                                                  */
+    const float* b_hh;        /* [3H]                                                     */
+    /* input side */
+    const float* emb;         /* [Vin][3H] = W_ih[:, :Vin]^T, or NULL                     */
+    const int32_t* ids;       /* [T][B] token ids (by time), or NULL                      */
+    const float* proj;        /* [B][3H] (row stride proj_ld; 0 = one broadcast row) / NULL */
+    long long proj_ld;
+    const float* dense;       /* [T][B][3H] (by time) or NULL                             */
+    const float* h0;          /* [B][H] or NULL (zeros)                                   */
+    int32_t reverse;          /* 1: run time backwards (bidirectional encoder, 2nd dir)   */
+    int32_t _pad0;
+    /* forward outputs */
+    float* hs;                /* [T][B][H]  (by time) hidden state after that time step   */
+    float* gates;             /* [T][B][4H] (r, z, n, gh_n) saved for BPTT, or NULL       */
+    float* h_final;           /* [B] rows of stride h_final_ld: last state, or NULL       */
+    long long h_final_ld;
+    /* backward inputs */
+    const float* dhs;         /* [T][B][H] (by time) grad wrt hs, or NULL                 */
+    const float* dh_final;    /* grad wrt h_final (row stride dh_final_ld), or NULL       */
+    long long dh_final_ld;
+    /* backward outputs */
+    float* dgh;               /* [T][B][3H] grad wrt gh = (dr_pre, dz_pre, dn_pre*r)      */
+    float* dgin;              /* [T][B][H]  grad wrt gi_n = dn_pre  (gi_r,gi_z share dgh) */
+    float* dh0;               /* [B][H] grad wrt h0 (always written)                      */
+    float* dh_carry;          /* [B][H] scratch                                           */
+} FnGruChain;
+
+/* `chains` is a HOST array.  All chains of one call share B, T, H. */
+int fn_gru_seq_fwd_f32(const FnGruChain* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                       size_t barrier_ws_bytes, void* stream);
+/* BPTT of the above (autograd of the reference's nn.GRU calls and of the Python GRUCell loop,
+ * trainer_gmm.py:249 loss.backward()).  Weight/bias/embedding gradients are finished by
+ * fn_gemm_f32 / fn_emb_grad_f32 / fn_time_sum_f32 on the dgh/dgin streams. */
+int fn_gru_seq_bwd_f32(const FnGruChain* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                       size_t barrier_ws_bytes, void* stream);
+/* How many CTAs one chain needs for hidden size H (host query; <=0 if H unsupported). */
+int fn_gru_seq_ctas_per_chain(int H);
+
+/* ------------------------------------------------------------------------------------------
+ * Token plumbing.
+ * ---------------------------------------------------------------------------------------- */
+/* one-hot (B,T,V) fp32 -> first-max index, time-major int32 [T][B]  (inverse of
+ * convert_to_one_hot, trainer_gmm.py:296-303; the reference feeds the dense one-hot to nn.GRU) */
+int fn_onehot_to_ids(const float* onehot, int B, int T, int V, int32_t* ids_tm, void* stream);
+/* int64 ids (B,T) -> dense one-hot (B,T,V) fp32  (convert_to_one_hot, trainer_gmm.py:296-303) */
+int fn_ids_to_onehot(const int64_t* ids, int B, int T, int V, float* onehot, void* stream);
+/* int64 ids (B,T) -> int32 time-major [T][B]; shift=1 gives the teacher-forced decoder input
+ * stream (start token at t=0, then ids[:, t-1]; gmm_model.py:120-121,139-142). */
+int fn_ids_to_time_major(const int64_t* ids, int B, int T, int shift, int start_token, int32_t* ids_tm,
+                         void* stream);
+/* dst[c][r] = src[r][c] (+= if accumulate)  -- W_ih[:, :V] <-> embedding-table layout */
+int fn_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols,
+                     int accumulate, void* stream);
+
+/* dst[i] += src[i]  (folds dh0 of the second decoder cell into the first cell's state gradient) */
+int fn_add_f32(float* dst, const float* src, long long n, void* stream);
+
+/* Embedding-table gradient: demb[v][c] = sum over (t,b) with ids[t][b]==v of dgi[t][b][c], where
+ * dgi = [dgh[:, :2H] | dgin].  Deterministic two-stage segmented reduction.  `scratch` needs
+ * fn_emb_grad_scratch_bytes().  (autograd of `onehot @ W_ih^T`, gmm_model.py:84,109,132-133) */
+size_t fn_emb_grad_scratch_bytes(int B, int T, int H, int V);
+int fn_emb_grad_f32(const int32_t* ids_tm, const float* dgh, const float* dgin, int B, int T, int H, int V,
+                    float* demb, void* scratch, size_t scratch_bytes, void* stream);
+/* Time sums of the BPTT gate gradients: dproj[b][c] = sum_t dgi[t][b][c] (gradient of the
+ * time-invariant input-side term: z-projection + b_ih) and dghsum[b][c] = sum_t dgh[t][b][c]
+ * (column-summed afterwards into the b_hh gradient).  Either output may be NULL. */
+int fn_time_sum_f32(const float* dgh, const float* dgin, int B, int T, int H, float* dproj, float* dghsum,
+                    void* stream);
+/* out[c] (+)= sum_r x[r][c]  (bias gradients); deterministic two-stage reduction. */
+size_t fn_col_sum_scratch_bytes(long long rows, int cols);
+int fn_col_sum_f32(const float* x, long long ld, long long rows, int cols, float* out, int accumulate,
+                   void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Soft-max heads and NLL.
+ * ---------------------------------------------------------------------------------------- */
+/* logits [T][B][V] (time-major) -> log-probs out (B,T,V) batch-major: F.log_softmax over the
+ * vocabulary, gmm_model.py:137 + torch.stack(x,1) :149. */
+int fn_vocab_logsoftmax_fwd(const float* logits_tm, int B, int T, int V, float* out_bm, void* stream);
+/* dlogits_tm = dout - exp(out) * rowsum(dout) */
+int fn_vocab_logsoftmax_bwd(const float* out_bm, const float* dout_bm, int B, int T, int V, float* dlogits_tm,
+                            void* stream);
+/* Fused train-step variant: mean NLL of the vocabulary head without materialising dout:
+ *   fwd: loss_rows[t*B+b] = -logp[target]; out_bm written only if non-NULL;
+ *   bwd: dlogits_tm = scale * (softmax - onehot(target))   (F.nll_loss, trainer_gmm.py:131-132) */
+int fn_vocab_nll_fwd(const float* logits_tm, const int64_t* target_bm, int B, int T, int V, float* out_bm,
+                     float* lse_tm, float* loss_rows, void* stream);
+int fn_vocab_nll_bwd(const float* logits_tm, const float* lse_tm, const int64_t* target_bm, const float* scale_dev,
+                     float scale_host, int B, int T, int V, float* dlogits_tm, void* stream);
+/* Sub-decoder heads: log-softmax over the TIME axis (dim=1 of (B,T,C); gmm_model.py:110,115).
+ * logits [T][B][C] -> out (B,T,C). */
+int fn_time_logsoftmax_fwd(const float* logits_tm, int B, int T, int C, float* out_bm, void* stream);
+int fn_time_logsoftmax_bwd(const float* out_bm, const float* dout_bm, int B, int T, int C, float* dlogits_tm,
+                           void* stream);
+/* F.nll_loss(logp.view(-1,C), target.view(-1), 'mean') (trainer_gmm.py:131-136): gather + mean. */
+int fn_nll_mean_fwd(const float* logp, const int64_t* target, long long rows, int C, float* loss, void* scratch,
+                    size_t scratch_bytes, void* stream);
+/* dlogp[row][target] (+)= dloss / rows ; all other entries zero (zero_fill=1 clears first). */
+int fn_nll_mean_bwd(const int64_t* target, long long rows, int C, const float* dloss, float* dlogp, int zero_fill,
+                    void* stream);
+size_t fn_reduce_scratch_bytes(long long n);
+/* out[0] = scale * sum(x[0..n)) , deterministic */
+int fn_sum_f32(const float* x, long long n, float scale, float* out, void* scratch, size_t scratch_bytes,
+               void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Latent block.
+ * ---------------------------------------------------------------------------------------- */
+/* scale = exp(pre)  (var_r(x).exp_(), gmm_model.py:86,91) and z = mu + scale*eps (repar, :229-235) */
+int fn_reparam_fwd(const float* mu, const float* pre_scale, const float* eps, long long n, float* scale, float* z,
+                   void* stream);
+/* dmu = dz + dmu_in ; dpre = (dz*eps + dscale_in) * scale */
+int fn_reparam_bwd(const float* dz, const float* dmu_in, const float* dscale_in, const float* eps,
+                   const float* scale, long long n, float* dmu, float* dpre, void* stream);
+/* approx_qy_x (gmm_model.py:194-218): logLogit[b][k] = -0.5*sum_d((z-mu_k)^2/exp(lv_k)+lv_k+ln2pi)+ln(1/K),
+ * qy = softmax_k, y = first argmax. */
+int fn_qy_x_fwd(const float* z, const float* mu_lookup, const float* logvar_lookup, int B, int Z, int K,
+                float* logLogit, float* qy, int64_t* y, void* stream);
+/* given dlogLogit, dqy: dz (B,Z), dmu_lookup (K,Z) (+= if accumulate) */
+int fn_qy_x_bwd(const float* z, const float* mu_lookup, const float* logvar_lookup, const float* qy,
+                const float* dlogLogit, const float* dqy, int B, int Z, int K, float* dz, float* dmu_lookup,
+                void* stream);
+/* GM-VAE KL block (trainer_gmm.py:140-194).  mode 0 = unsupervised, 1 = supervised (y_label).
+ * out[0] = kld_lat (sum_k mean_b(mean_z KL(q||p_k) * qy[b,k]))   [sup: mean_b mean_z KL(q||p_y)]
+ * out[1] = kld_cls ((mean_k(qy*log_softmax(logLogit)) - ln(1/K)).mean())  [sup: 0]
+ * out[2] = label_clf (sup only: CrossEntropyLoss applied to the probabilities qy)  [unsup: 0]
+ * p_k = Normal(mu_k, scale = exp(logvar_k))  (sic: exp(logvar) used as scale, :156-157). */
+int fn_gm_kl_fwd(const float* mu, const float* scale, const float* mu_lookup, const float* logvar_lookup,
+                 const float* qy, const float* logLogit, const int64_t* y_label, int mode, int B, int Z, int K,
+                 float* out3, void* stream);
+/* grads wrt (mu, scale, qy, logLogit, mu_lookup) given dout3 (device, 3 floats). */
+int fn_gm_kl_bwd(const float* mu, const float* scale, const float* mu_lookup, const float* logvar_lookup,
+                 const float* qy, const float* logLogit, const int64_t* y_label, int mode, int B, int Z, int K,
+                 const float* dout3, float* dmu, float* dscale, float* dqy, float* dlogLogit, float* dmu_lookup,
+                 void* stream);
+/* vanilla VAE: out[0] = mean_{B,Z} KL(N(mu,scale) || N(0,1))  (trainer.py:104-109) */
+int fn_std_kl_fwd(const float* mu, const float* scale, long long n, float* out, void* stream);
+int fn_std_kl_bwd(const float* mu, const float* scale, long long n, const float* dout, float* dmu, float* dscale,
+                  void* stream);
+/* Pati et al. latent regularisation (trainer_gmm.py:199-217): l = mean_{i,j}(tanh(z0_i - z0_j) -
+ * sign(a_i - a_j))^2 on latent dim 0; attribute differences are taken in float64 as the reference's
+ * host numpy does.  z0 has element stride z_ld.  Also returns dl/dz0 (B floats) for the backward. */
+int fn_latent_reg_fwd(const float* z, long long z_ld, const double* attr, int B, float* loss, float* dz0,
+                      float* row_scratch /* B floats */, void* stream);
+/* dz (B,Z) = 0 except column 0 = dloss[0] * dz0 */
+int fn_latent_reg_bwd(const float* dz0, const float* dloss, int B, int Z, float* dz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: clip_grad_norm_(params, max_norm) + Adam.step() on flat buffers
+ * (trainer_gmm.py:250-251; torch clip_grad.py: coef = max_norm/(norm+1e-6) clamped to 1;
+ *  optim.Adam defaults betas (0.9,0.999) eps 1e-8, no weight decay / amsgrad).
+ * ---------------------------------------------------------------------------------------- */
+/* norm_out[0] = ||g||_2 over n elements (fp32 accumulate in double). */
+int fn_grad_norm(const float* g, long long n, float* norm_out, void* scratch, size_t scratch_bytes, void* stream);
+/* p,m,v updated in place; g scaled by the clip coefficient computed from *norm (device). step >= 1. */
+int fn_clip_adam(float* p, const float* g, float* m, float* v, long long n, const float* norm, float max_norm,
+                 float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FADERNETS_B200_H */

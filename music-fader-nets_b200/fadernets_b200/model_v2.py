@@ -1,0 +1,2 @@
+"""Same module name as the reference's model_v2.py: `from model_v2 import MusicAttrRegVAE`."""
+from .models import MusicAttrRegVAE  # noqa: F401
