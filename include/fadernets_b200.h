@@ -52,6 +52,18 @@ int fn_gemm_f32(const float* A, long long sam, long long sak, const float* B, lo
                 float* C, long long ldc, const float* bias, int M, int N, int K, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * bf16 tensor-core GEMM (tcgen05.mma, fp32 accumulation in TMEM, TMA-fed 128B-swizzled smem ring).
+ *   C[M][N] (ldc; fp32 or bf16) = (accumulate ? C : 0) + A * B + (bias ? bias[n] : 0)
+ *   a_mn_major = 0: A is stored [M][K] (lda);  1: A is stored transposed, [K][M] (lda)
+ *   b_mn_major = 0: B is stored [N][K] (ldb) (nn.Linear weight layout);  1: stored [K][N] (ldb)
+ * lda/ldb are in elements and must be multiples of 8 (16-byte TMA pitch); bases 16-byte aligned.
+ * Same call sites as fn_gemm_f32, used by the bf16 configurations (BASELINE configs 3-5).
+ * ---------------------------------------------------------------------------------------- */
+int fn_tc_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                    void* C, long long ldc, int c_bf16, const float* bias, int M, int N, int K, int accumulate,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Persistent time-loop GRU ("gate block": recurrent GEMM + sigma/tanh/Hadamard per step).
  * One launch runs `n_chains` independent recurrences; each chain is split over hidden-unit
  * slices (one CTA per slice, W_hh slice resident in shared memory for all T steps) with a

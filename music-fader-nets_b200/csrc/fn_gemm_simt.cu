@@ -193,7 +193,7 @@ int launch(const float* A, long long sam, long long sak, const float* B, long lo
 extern "C" int fn_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk,
                            long long sbn, float* C, long long ldc, const float* bias, int M, int N, int K,
                            int accumulate, void* stream) {
-    FN_REQUIRE(A && B && C, "fn_gemm_f32: null operand");
+    FN_REQUIRE(C && (K == 0 || (A && B)), "fn_gemm_f32: null operand");
     FN_REQUIRE(M >= 0 && N >= 0 && K >= 0, "fn_gemm_f32: negative size");
     FN_REQUIRE(sam == 1 || sak == 1, "fn_gemm_f32: A needs a unit stride (sam=%lld sak=%lld)", sam, sak);
     FN_REQUIRE(sbk == 1 || sbn == 1, "fn_gemm_f32: B needs a unit stride (sbk=%lld sbn=%lld)", sbk, sbn);

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "fn_abi_version": (I, []),
     "fn_device_info": (I, [C.POINTER(I)] * 4),
     "fn_gemm_f32": (I, [V, LL, LL, V, LL, LL, V, LL, V, I, I, I, I, V]),
+    "fn_tc_gemm_bf16": (I, [V, LL, I, V, LL, I, V, LL, I, V, I, I, I, I, V]),
     "fn_gru_seq_fwd_f32": (I, [C.POINTER(FnGruChain), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_bwd_f32": (I, [C.POINTER(FnGruChain), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_ctas_per_chain": (I, [I]),

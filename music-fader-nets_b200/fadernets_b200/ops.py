@@ -157,7 +157,7 @@ class GruGroupFn(torch.autograd.Function):
     def forward(ctx, specs: List[ChainSpec], B: int, T: int, H: int, final_widths, *tensors):
         dev = tensors[0].device
         require_cuda(*tensors)
-        need_grad = torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad)
         chains = (FnGruChain * len(specs))()
         finals = [torch.empty((B, wd), dtype=F32, device=dev) for wd in final_widths]
         keep = []      # per chain dict of buffers
