@@ -136,11 +136,12 @@ def run_ours(args):
     model = model.to(dev).train()
     model.host_rng = True
 
-    def grad_sync(flat_grad):
-        dist.all_reduce(flat_grad)                     # one NCCL all-reduce per step (sum), then mean
-        flat_grad.mul_(1.0 / world)
-
-    opt = fn.FusedAdam(model, lr=1e-3, grad_sync=grad_sync if world > 1 else None)
+    from fadernets_b200 import parallel
+    if world > 1:
+        model.flatten_parameters_()
+        parallel.broadcast_parameters(model, src=0)
+    # one NCCL all-reduce (sum -> mean) of the flat gradient buffer per step, between backward and clip+Adam
+    opt = fn.FusedAdam(model, lr=1e-3, grad_sync=parallel.GradAllReduce() if world > 1 else None)
     tr = trainer_gmm if variant == "gmvae" else trainer
     if variant == "gmvae":
         tr.configure(model, opt, {"beta": 0.2, "lr": 1e-3})
