@@ -27,9 +27,11 @@ import torch
 
 WORKLOADS = {
     # name: (variant, B per GPU, T, H, Z, K, precision)
-    "c1": ("vae", 4, 128, 256, 128, 0, "fp32"),
-    "c2": ("gmvae", 64, 256, 512, 128, 2, "fp32"),
-    "c3": ("gmvae", 256, 512, 1024, 128, 2, "fp32"),
+    "c1": ("vae", 4, 128, 256, 128, 0, "f32"),
+    "c2": ("gmvae", 64, 256, 512, 128, 2, "f32"),
+    "c2_bf16": ("gmvae", 64, 256, 512, 128, 2, "bf16"),
+    "c3": ("gmvae", 256, 512, 1024, 128, 2, "bf16"),
+    "c3_f32": ("gmvae", 256, 512, 1024, 128, 2, "f32"),
 }
 STEP0 = 20000          # beta0 = beta = 0.2: every KL term is live
 
@@ -135,6 +137,7 @@ def run_ours(args):
         model = fn.MusicAttrRegVAE(342, 3, 16, 24, H, Z, 32)
     model = model.to(dev).train()
     model.host_rng = True
+    model.set_precision(prec)
 
     from fadernets_b200 import parallel
     if world > 1:
@@ -223,7 +226,7 @@ def run_ours(args):
         "metric": "sequences/sec GM-VAE train step", "value": round(value, 2), "unit": "sequences/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": prec, "data": "synthetic",
         "config": {"workload": f"{args.workload}: Music{'AttrRegGMVAE' if variant == 'gmvae' else 'AttrRegVAE'} "
                                f"train step, batch {B}/GPU x seq_len {T}, hidden {H}, z {Z}, K {K}, {prec}",
                    "global_batch": gbatch, "seq_len": T, "hidden": H, "parallelism": f"dp{world}",
@@ -233,12 +236,13 @@ def run_ours(args):
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": round(sec_e2e / args.steps * 1e3, 3)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "gru_fwd_kernel + gru_bwd_kernel (persistent recurrent GEMM + gates)",
+        "roofline": {"kernel": ("gru_tc_kernel fwd+bwd (persistent tcgen05 recurrent GEMM + gates)" if prec == "bf16" else
+                                "gru_fwd_kernel + gru_bwd_kernel (persistent fp32 SIMT recurrent GEMM + gates)"),
                      "bound": "tensor", "achieved": round(achieved, 3) if achieved else None,
                      "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                      "frac": round(achieved / peaks["tf_sust"], 5) if achieved else None, "traffic": None,
-                     "peak_source": peaks["src"] + " bf16 sustained (kernel timed inside a long step); this round's "
-                                                   "kernel is the fp32 SIMT parity path, not yet tcgen05",
+                     "peak_source": peaks["src"] + " cuBLAS bf16 sustained (kernel timed inside a long step)" +
+                                    ("" if prec == "bf16" else "; fp32 SIMT exact-parity path (FMA pipe, no tensor cores)"),
                      "flops_per_launch_group": gru_flops, "ms_per_step_in_kernel": round(gru_ms, 3) if gru_ms else None,
                      "step_flops": flops_per_token(H) * tokens,
                      "step_frac_of_peak": round(flops_per_token(H) * tokens * world / (sec / args.steps) / 1e12 / (peaks["tf_sust"] * world), 5)},
@@ -259,7 +263,7 @@ def cpu_reference(workload, steps, warmup, sample_batch=None):
     variant, B, T, H, Z, K, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = sample_batch or {"c1": 4, "c2": 8, "c3": 4}[workload]
+    Bs = sample_batch or {"c1": 4, "c2": 8, "c2_bf16": 8, "c3": 4, "c3_f32": 4}[workload]
     w = fo.init_weights(H, Z, variant, max(K, 1), seed=0)
     st = fo.AdamState(w)
     batch = fo.synth_batch(Bs, T, seed=0)

@@ -118,6 +118,58 @@ int fn_gru_seq_bwd_f32(const FnGruChain* chains, int n_chains, int B, int T, int
 int fn_gru_seq_ctas_per_chain(int H);
 
 /* ------------------------------------------------------------------------------------------
+ * The same gate block on the 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32
+ * accumulation in TMEM, weight slice resident in shared memory, state slabs streamed by TMA).
+ * Everything is indexed BY TIME; step s of a chain works on time tau = s, or tau = T-1-s for a
+ * reverse chain.  hsx has T+1 slabs of [B][H]: a forward chain reads its initial state from slab 0
+ * and writes h_tau to slab tau+1; a reverse chain reads slab T and writes h_tau to slab tau.  The
+ * caller fills the initial-state slab.  B <= 256 rows per chain (larger batches: several chains).
+ * Same reference call sites as fn_gru_seq_*_f32; used by the bf16 configurations (BASELINE 3-5).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct FnGruChainBf16 {
+    const void* w_hh;         /* bf16 [3H][H]            (forward)                            */
+    const void* w_hh_t;       /* bf16 [H][3H] = W_hh^T   (backward)                           */
+    const float* b_hh;        /* fp32 [3H]                                                    */
+    const float* emb;         /* fp32 [Vin][3H] = W_ih[:, :Vin]^T, or NULL                    */
+    const int32_t* ids;       /* [T][B] token ids by time, or NULL                            */
+    const float* proj;        /* fp32 [B][3H] (row stride proj_ld; 0 = one broadcast row) / NULL */
+    long long proj_ld;
+    const void* dense;        /* bf16 [T][B][3H] by time, or NULL                             */
+    int32_t reverse;
+    int32_t dhs_f32;          /* dtype of dhs: 0 = bf16, 1 = fp32                             */
+    void* hsx;                /* bf16 [T+1][B][H] (see above)                                 */
+    void* gates;              /* bf16 [T][B][4H]: r, z, n, W_hn h + b_hn  (NULL = inference)  */
+    float* h_final;           /* fp32 rows of stride h_final_ld: state after the last step / NULL */
+    long long h_final_ld;
+    const void* dhs;          /* [T][B][H] by time: grad wrt h_tau, or NULL                   */
+    const float* dh_final;    /* fp32 grad wrt h_final (row stride dh_final_ld), or NULL      */
+    long long dh_final_ld;
+    void* dg;                 /* bf16 [T][B][4H]: dr_pre, dz_pre, dn_pre, dn_pre*r (cols [0,3H) = grad wrt
+                                 the input-side pre-activations, [0,2H) + [3H,4H) = grad wrt W_hh h + b_hh) */
+    float* dh0;               /* fp32 [B][H] grad wrt the initial state                       */
+} FnGruChainBf16;
+int fn_gru_seq_fwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                        size_t barrier_ws_bytes, void* stream);
+int fn_gru_seq_bwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                        size_t barrier_ws_bytes, void* stream);
+
+/* fp32 -> bf16 with arbitrary strides: dst[r*ld_dst + c] = bf16(src[r*s_r + c*s_c]) (s_r/s_c in
+ * elements; s_c != 1 gives the transposed copy W_hh^T used by BPTT). */
+int fn_cast_bf16(const float* src, long long s_r, long long s_c, void* dst, long long ld_dst, long long rows,
+                 long long cols, void* stream);
+/* int32 ids [rows] -> bf16 one-hot [rows][ld] (columns >= V zero): the MN-major operand of the
+ * tensor-core form of autograd's `onehot^T @ dgi` (gmm_model.py:84,109,132-133). */
+int fn_ids_to_onehot_bf16(const int32_t* ids, long long rows, int V, long long ld, void* onehot, void* stream);
+/* bf16 variant of fn_time_sum_f32 over dg [T][B][4H]: dproj = sum_t dg[:, :3H],
+ * dghsum = sum_t [dg[:, :2H] | dg[:, 3H:]]. */
+int fn_time_sum_bf16(const void* dg, int B, int T, int H, float* dproj, float* dghsum, void* stream);
+/* dst[i] = bf16(float(dst[i]) + src[i])  (bf16 twin of fn_add_f32) */
+int fn_add_f32_to_bf16(void* dst, const float* src, long long n, void* stream);
+/* out[c] (+)= sum_r x[r][c] for a bf16 matrix (bias gradients of the tensor-core linears). */
+int fn_col_sum_bf16(const void* x, long long ld, long long rows, int cols, float* out, int accumulate,
+                    void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Token plumbing.
  * ---------------------------------------------------------------------------------------- */
 /* one-hot (B,T,V) fp32 -> first-max index, time-major int32 [T][B]  (inverse of

@@ -1,15 +1,29 @@
-// Persistent time-loop GRU on tcgen05 (bf16 operands, fp32 accumulation in TMEM): fn_gru_seq_fwd_bf16 /
-// fn_gru_seq_bwd_bf16.  Same decomposition as the fp32 path (fn_gru_simt.cu): one CTA owns U hidden units
-// of one chain for all T steps and keeps its weight slice RESIDENT in 128B-swizzled shared memory
-// (forward: the 3U x H rows of W_hh; BPTT: the U x 3H rows of W_hh^T), loaded once by TMA.  Per step
-//   warp 0      : waits for the chain's step counter, then streams the [B][K] state slab (K = H forward,
-//                 3H backward) through a TMA ring of 128 x 64 K-major tiles;
-//   warp 1      : one thread issues tcgen05.mma (M=128 batch rows, N=3U or U, K=16) into a per-batch-tile
-//                 TMEM accumulator;
-//   warps 2..9  : gate epilogue straight out of TMEM (tcgen05.ld): token gather, sigma/tanh/Hadamard, state
-//                 and gate saves (forward) or the gate-gradient chain rule (backward); then publish the step.
-// Everything is indexed BY STEP (slab s+1 of hsx = state after step s; slab 0 = h0), so reverse chains
-// simply get reversed token / dense streams from the host.
+// Persistent time-loop GRU gate block on tcgen05 (bf16 operands, fp32 accumulation in TMEM):
+// fn_gru_seq_fwd_bf16 / fn_gru_seq_bwd_bf16.
+//
+// Decomposition.  A chain (one recurrence) is cut into H/U hidden-unit slices; ONE CTA owns one slice of
+// one chain for all T steps and keeps its weight slice RESIDENT in 128B-swizzled shared memory, loaded
+// once by TMA (forward: the 3U rows of W_hh that produce its units' r/z/n gates; BPTT: the U rows of
+// W_hh^T that produce its units' state gradient).  The batch is cut into 128-row tiles (the MMA M); the
+// tiles of a chain are INDEPENDENT recurrences that share the resident weights, so the CTA ping-pongs
+// between them: while the gate epilogue of tile 0 runs, the tensor core works on tile 1.
+//
+// Per (step, batch tile):
+//   warp 0  (1 thread)  waits until every slice of the chain has published the previous step of this
+//                       batch tile (release/acquire counter in global memory), then streams the
+//                       [128][K] state slab (K = H forward, 3H backward) through a TMA ring;
+//   warp 1  (1 thread)  issues tcgen05.mma (M = 128 batch rows, N = 3U | U, K = 16) into the tile's
+//                       TMEM accumulator and commits ring slots / the accumulator to mbarriers;
+//   warps 2..9          gate epilogue straight out of TMEM (tcgen05.ld): token-embedding gather,
+//                       sigma / tanh / Hadamard, state + gate saves (forward) or the gate-gradient chain
+//                       rule (backward); the running state (forward) / carried gradient (backward) of
+//                       the thread's (row, units) stays in REGISTERS for the whole sequence; the
+//                       time-invariant input projection (+ biases) lives in TMEM next to the accumulator.
+// Everything in memory is indexed BY TIME: step s of a chain works on time tau = s (forward in time) or
+// tau = T-1-s (reverse chain).  hsx has T+1 slabs: a forward chain keeps its initial state in slab 0 and
+// h_tau in slab tau+1; a reverse chain keeps its initial state in slab T and h_tau in slab tau -- so
+// "the state before step s" is slab tau (forward) / tau+1 (reverse) and lines up row for row with
+// gates[tau] / dg[tau] in the batched weight-gradient GEMMs.
 #include "fn_tc.cuh"
 
 namespace {
@@ -17,29 +31,32 @@ namespace {
 constexpr int kMaxChainsTc = 4;
 constexpr int kThreadsTc = 320;           // 2 control warps + 8 epilogue warps
 constexpr int kEpiThreads = 256;
-constexpr int kAStages = 2;
-constexpr int kATile = 128 * 64 * 2;      // 16 KB: 128 batch rows x 64 K
-constexpr int kMaxAcc = 8;
+constexpr int kATile = 128 * 64 * 2;      // 16 KB: 128 batch rows x 64 K (bf16), one 128B-swizzle atom wide
+constexpr int kMaxStages = 8;
+constexpr int kMaxNbt = 2;
 
 struct TcChain {
     CUtensorMap tmW;       // resident operand: fwd W_hh [3H][H]; bwd W_hh^T [H][3H]   (box 64 x U)
     CUtensorMap tmA;       // streamed operand, 3-D [slabs][B][K]                      (box 64 x 128 x 1)
-    // forward
     const float* b_hh; const float* emb; const int32_t* ids; const float* proj; long long proj_ld;
-    const __nv_bfloat16* dense; const float* h0;
-    __nv_bfloat16* hsx; float* hcur; __nv_bfloat16* gates; float* h_final; long long h_final_ld;
-    // backward
-    const __nv_bfloat16* dhs; const float* dh_final; long long dh_final_ld;
-    __nv_bfloat16* dgh; __nv_bfloat16* dgin; float* dh0; float* carry;
+    const __nv_bfloat16* dense;
+    __nv_bfloat16* hsx; __nv_bfloat16* gates; float* h_final; long long h_final_ld;
+    const void* dhs; const float* dh_final; long long dh_final_ld;
+    __nv_bfloat16* dg; float* dh0;
+    int reverse, dhs_f32;
 };
 
 struct TcLaunch {
     TcChain c[kMaxChainsTc];
-    unsigned* bar;
-    int n_chains, nslices, B, T, H;
+    unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
+    int n_chains, nslices, B, T, H, stages;
 };
 
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+// ---- TMEM <-> registers, 32 lanes x W consecutive fp32 columns (thread i <-> lane base + i) --------
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -52,292 +69,407 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int W>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+          "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void ld16(const float* __restrict__ p, float (&v)[16]) {
+// ---- W-wide vector loads / stores (W = 8 or 16 elements, 16-byte aligned) ----------------------------
+template <int W>
+__device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[W]) {      // read-only fp32
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < W / 4; ++i) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
     }
 }
-__device__ __forceinline__ void add16(const float* __restrict__ p, float (&v)[16]) {
+template <int W>
+__device__ __forceinline__ void stf(float* p, const float (&v)[W]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
-        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    for (int i = 0; i < W / 4; ++i)
+        *(reinterpret_cast<float4*>(p) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+// packed bf16: W/2 32-bit words
+template <int W>
+__device__ __forceinline__ void ldb_raw(const __nv_bfloat16* p, uint32_t (&w)[W / 2], bool coherent) {
+#pragma unroll
+    for (int i = 0; i < W / 8; ++i) {
+        const uint4 t = coherent ? __ldcg(reinterpret_cast<const uint4*>(p) + i) : __ldg(reinterpret_cast<const uint4*>(p) + i);
+        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
     }
 }
-__device__ __forceinline__ void ld16_cg(const float* p, float (&v)[16]) {
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+template <int W>
+__device__ __forceinline__ void unpack(const uint32_t (&w)[W / 2], float (&v)[W]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(p) + i);
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-    }
+    for (int i = 0; i < W / 2; ++i) { v[2 * i] = bf_lo(w[i]); v[2 * i + 1] = bf_hi(w[i]); }
 }
-__device__ __forceinline__ void st16_cg(float* p, const float (&v)[16]) {
+template <int W>
+__device__ __forceinline__ void stb(__nv_bfloat16* p, const float (&v)[W]) {
+    uint32_t w[W / 2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        __stcg(reinterpret_cast<float4*>(p) + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-}
-__device__ __forceinline__ void ld16_bf(const __nv_bfloat16* p, float (&v)[16]) {      // 32 B, L2 (written by peers / this kernel)
-    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p)), b = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v[2 * i] = __uint_as_float(w[i] << 16);
-        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-}
-__device__ __forceinline__ void add16_bf(const __nv_bfloat16* p, float (&v)[16]) {
-    float t[16];
-    ld16_bf(p, t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += t[i];
-}
-__device__ __forceinline__ void st16_bf(__nv_bfloat16* p, const float (&v)[16]) {
-    uint32_t w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < W / 2; ++i) {
         const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         w[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    __stcg(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
-    __stcg(reinterpret_cast<uint4*>(p) + 1, make_uint4(w[4], w[5], w[6], w[7]));
+#pragma unroll
+    for (int i = 0; i < W / 8; ++i)
+        __stcg(reinterpret_cast<uint4*>(p) + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
-// U = hidden units per CTA.  Forward: N = 3U gate columns, K = H.  Backward: N = U, K = 3H.
-template <int U, bool BWD>
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    // tanh(x) = 2*sigmoid(2x) - 1 ; exact to ~1e-6 relative with the SFU exp, far below bf16 resolution
+    return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f;
+}
+
+// one thread publishes a finished (step, batch tile) of this slice to the other slices of the chain
+__device__ __forceinline__ void publish(unsigned* ctr) {
+    epi_barrier();
+    if (threadIdx.x == 64) {
+        asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy stores -> later TMA (async-proxy) reads
+        __threadfence();
+        fn_red_release(ctr, 1u);
+    }
+}
+
+struct Smem {
+    uint8_t* W; uint8_t* A;
+    uint64_t *full, *empty, *acc_full, *acc_empty, *wbar;
+    uint32_t* tmem_slot;
+    float* bias;
+};
+__device__ __forceinline__ Smem carve(uint8_t* smem_raw, int w_bytes, int stages) {
+    Smem s;
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    s.W = base;
+    s.A = base + w_bytes;                                     // w_bytes is a multiple of 1024
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.A + (size_t)stages * kATile);
+    s.full = bars; s.empty = bars + kMaxStages; s.acc_full = s.empty + kMaxStages; s.acc_empty = s.acc_full + kMaxNbt;
+    s.wbar = s.acc_empty + kMaxNbt;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.wbar + 1);
+    s.bias = reinterpret_cast<float*>(s.tmem_slot + 2);
+    return s;
+}
+
+// =====================================================================================================
+// U = hidden units per CTA, NBT = 128-row batch tiles per chain.  BWD = false: N = 3U gate columns,
+// K = H.  BWD = true: N = U, K = 3H (A = gate gradients of the following step, pitch 4H).
+// =====================================================================================================
+template <int U, int NBT, bool BWD>
 __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
     constexpr int N = BWD ? U : 3 * U;
+    constexpr int UT = U / 2;                                  // units per epilogue thread
+    constexpr uint32_t kAccCols = NBT * N;                     // accumulators; forward: + NBT*N projection columns
+    constexpr uint32_t kNeedCols = BWD ? kAccCols : 2 * kAccCols;
+    constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
+    static_assert(kNeedCols <= 512, "TMEM columns");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int H = P.H, B = P.B, T = P.T;
+    const int H = P.H, B = P.B, T = P.T, S = P.stages;
     const int K = BWD ? 3 * H : H;
     const int nkc = K / 64;
-    const int w_chunk_bytes = N * 128;                        // one 64-wide K chunk of the resident operand
-    uint8_t* Wsm = smem;
-    uint8_t* Asm = smem + (size_t)nkc * w_chunk_bytes;        // kAStages x 16 KB (1024-aligned: N*128 is a multiple of 1024 for U % 8 == 0 ... checked on host)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Asm + kAStages * kATile);
-    uint64_t* full = bars;                   // [kAStages]
-    uint64_t* empty = bars + kAStages;       // [kAStages]
-    uint64_t* acc_full = empty + kAStages;   // [kMaxAcc]
-    uint64_t* acc_empty = acc_full + kMaxAcc;
-    uint64_t* wbar = acc_empty + kMaxAcc;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-    float* bias_sm = reinterpret_cast<float*>(tmem_slot + 2);   // [3U] b_hh slice (forward)
+    const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
+    const Smem sm = carve(smem_raw, nkc * w_chunk_bytes, S);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
     const TcChain& c = P.c[chain];
     unsigned* gbar = P.bar + chain * 16;
     const int u0 = slice * U;
-    const int nbt = (B + 127) / 128;
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&c.tmW);
         tc::prefetch_tmap(&c.tmA);
-        for (int i = 0; i < kAStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kMaxAcc; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 8); }
-        tc::mbar_init(wbar, 1);
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], 8); }
+        tc::mbar_init(sm.wbar, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tc::tmem_alloc(sm.tmem_slot, kTmemCols);
     if (!BWD && threadIdx.x >= 64) {
-        for (int i = threadIdx.x - 64; i < 3 * U; i += kEpiThreads) bias_sm[i] = c.b_hh[(i / U) * H + u0 + (i % U)];
+        for (int i = threadIdx.x - 64; i < 3 * U; i += kEpiThreads) sm.bias[i] = c.b_hh[(i / U) * H + u0 + (i % U)];
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *sm.tmem_slot;
 
-    // step schedule.  forward: s = 0..T-1, A slab = s (state before the step).
-    // backward: s = T-1..-1, A slab = s+1 (gate gradient of the following step); s = T-1 has no product.
+    // iteration i: forward step s = i (A slab = s: the state before the step);
+    // backward s = T-1-i for i = 0..T (s = -1 finishes dh0); the product of iteration i >= 1 reads slab s+1 of dg.
     const int n_iters = BWD ? T + 1 : T;
 
     if (warp == 0) {
         if (lane == 0) {
-            // resident operand
-            tc::mbar_arrive_expect_tx(wbar, (uint32_t)(nkc * w_chunk_bytes));
+            tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(nkc * w_chunk_bytes));
             for (int kc = 0; kc < nkc; ++kc) {
                 if (!BWD) {
                     for (int g = 0; g < 3; ++g)
-                        tc::tma_load_2d(Wsm + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, wbar, kc * 64, g * H + u0);
+                        tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, sm.wbar, kc * 64, g * H + u0);
                 } else {
-                    tc::tma_load_2d(Wsm + (size_t)kc * w_chunk_bytes, &c.tmW, wbar, kc * 64, u0);
+                    tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes, &c.tmW, sm.wbar, kc * 64, u0);
                 }
             }
             uint32_t it = 0;
-            for (int i = 0; i < n_iters; ++i) {
-                const int s = BWD ? T - 1 - i : i;
-                const bool has_a = BWD ? (i > 0) : true;
-                if (!has_a) continue;
-                if (i > 0) {
-                    fn_spin_until(gbar, (unsigned)(P.nslices * i));
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                }
-                const int slab = BWD ? s + 1 : s;
-                for (int bt = 0; bt < nbt; ++bt)
-                    for (int kc = 0; kc < nkc; ++kc, ++it) {
-                        const int st = it % kAStages;
-                        tc::mbar_wait(&empty[st], ((it / kAStages) & 1) ^ 1);
-                        tc::mbar_arrive_expect_tx(&full[st], kATile);
-                        tc::tma_load_3d(Asm + st * kATile, &c.tmA, &full[st], kc * 64, bt * 128, slab);
+            for (int i = BWD ? 1 : 0; i < n_iters; ++i) {
+                // forward: the state before step s=i;  backward (s = T-1-i): the gate gradient of step s+1
+                const int slab = BWD ? (c.reverse ? i - 1 : T - i) : (c.reverse ? T - i : i);
+                for (int bt = 0; bt < NBT; ++bt) {
+                    if (i > 0) {
+                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i));
+                        asm volatile("fence.proxy.async;" ::: "memory");
                     }
+                    for (int kc = 0; kc < nkc; ++kc, ++it) {
+                        const int st = it % S;
+                        tc::mbar_wait(&sm.empty[st], ((it / S) & 1) ^ 1);
+                        tc::mbar_arrive_expect_tx(&sm.full[st], kATile);
+                        // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
+                        const int col = (BWD && kc * 64 >= 2 * H) ? kc * 64 + H : kc * 64;
+                        tc::tma_load_3d(sm.A + (size_t)st * kATile, &c.tmA, &sm.full[st], col, bt * 128, slab);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
-            tc::mbar_wait(wbar, 0);
+            tc::mbar_wait(sm.wbar, 0);
             uint32_t it = 0, uses = 0;
-            for (int i = 0; i < n_iters; ++i) {
-                const bool has_a = BWD ? (i > 0) : true;
-                if (!has_a) continue;
-                for (int bt = 0; bt < nbt; ++bt) {
-                    tc::mbar_wait(&acc_empty[bt], (uses & 1) ^ 1);
+            for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
+                for (int bt = 0; bt < NBT; ++bt) {
+                    tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
                     tc::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
                     for (int kc = 0; kc < nkc; ++kc, ++it) {
-                        const int st = it % kAStages;
-                        tc::mbar_wait(&full[st], (it / kAStages) & 1);
+                        const int st = it % S;
+                        tc::mbar_wait(&sm.full[st], (it / S) & 1);
                         tc::tc_fence_after();
-                        const uint32_t sa = tc::smem_u32(Asm + st * kATile);
-                        const uint32_t sb = tc::smem_u32(Wsm + (size_t)kc * w_chunk_bytes);
+                        const uint32_t sa = tc::smem_u32(sm.A + (size_t)st * kATile);
+                        const uint32_t sb = tc::smem_u32(sm.W + (size_t)kc * w_chunk_bytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             tc::umma_f16(d_tmem, tc::make_sdesc(sa + k * 32, 16, 1024), tc::make_sdesc(sb + k * 32, 16, 1024),
                                          idesc, (kc | k) != 0);
-                        tc::umma_commit(&empty[st]);
+                        tc::umma_commit(&sm.empty[st]);
                     }
-                    tc::umma_commit(&acc_full[bt]);
+                    tc::umma_commit(&sm.acc_full[bt]);
                 }
-                ++uses;
             }
         }
     } else {
         // ------------------------------- epilogue warps --------------------------------------------
-        const int ew = warp - 2;                 // 0..7
-        const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                // which half of the unit chunks
-        constexpr int NCH = U / 16;              // 16-unit chunks
-        uint32_t uses = 0;
-        for (int i = 0; i < n_iters; ++i) {
-            const int s = BWD ? T - 1 - i : i;
-            const bool has_a = BWD ? (i > 0) : true;
-            for (int bt = 0; bt < nbt; ++bt) {
-                if (has_a) {
-                    tc::mbar_wait(&acc_full[bt], uses & 1);
-                    tc::tc_fence_after();
-                }
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read (warp id % 4)
+        const int half = (warp - 2) >> 2;        // which half of the slice's units
+        const int uu = half * UT;                // unit offset inside the slice
+        const int u = u0 + uu;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+
+        if constexpr (!BWD) {
+            float hreg[NBT][UT];
+            // time-invariant part of the gate pre-activations -> TMEM columns [kAccCols + bt*N, +N)
+#pragma unroll
+            for (int bt = 0; bt < NBT; ++bt) {
                 const int b = bt * 128 + q * 32 + lane;
                 const bool row_ok = b < B;
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bt * N);
-                for (int ch = half; ch < NCH; ch += 2) {
-                    const int uu = ch * 16;                  // unit offset inside the slice
-                    const int u = u0 + uu;
-                    if (!BWD) {
-                        float ar[16], az[16], an[16];
-                        tmem_ld_32x16(trow + uu, ar);
-                        tmem_ld_32x16(trow + U + uu, az);
-                        tmem_ld_32x16(trow + 2 * U + uu, an);
-                        if (row_ok) {
-                            float gr[16], gz[16], gn[16], hp[16];
+                float pr[UT], pz[UT], pn[UT];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) { gr[j] = 0.f; gz[j] = 0.f; gn[j] = 0.f; hp[j] = 0.f; }
-                            const long long row = (long long)s * B + b;
-                            if (c.emb) {
-                                const float* e = c.emb + (long long)c.ids[row] * 3 * H + u;
-                                add16(e, gr); add16(e + H, gz); add16(e + 2 * H, gn);
-                            }
-                            if (c.proj) {
-                                const float* pj = c.proj + (long long)b * c.proj_ld + u;
-                                add16(pj, gr); add16(pj + H, gz); add16(pj + 2 * H, gn);
-                            }
-                            if (c.dense) {
-                                const __nv_bfloat16* dn = c.dense + row * 3 * H + u;
-                                add16_bf(dn, gr); add16_bf(dn + H, gz); add16_bf(dn + 2 * H, gn);
-                            }
-                            if (i > 0) ld16_cg(c.hcur + (long long)b * H + u, hp);
-                            else if (c.h0) ld16(c.h0 + (long long)b * H + u, hp);
-                            float hn[16], sr[16], sz[16], sn[16], sg[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float ghn = an[j] + bias_sm[2 * U + uu + j];
-                                const float r = fn_sigmoid(gr[j] + ar[j] + bias_sm[uu + j]);
-                                const float z = fn_sigmoid(gz[j] + az[j] + bias_sm[U + uu + j]);
-                                const float n = tanhf(gn[j] + r * ghn);
-                                hn[j] = (1.f - z) * n + z * hp[j];
-                                sr[j] = r; sz[j] = z; sn[j] = n; sg[j] = ghn;
-                            }
-                            st16_cg(c.hcur + (long long)b * H + u, hn);
-                            st16_bf(c.hsx + ((long long)(s + 1) * B + b) * H + u, hn);
-                            if (c.gates) {
-                                __nv_bfloat16* gsv = c.gates + row * 4 * H + u;
-                                st16_bf(gsv, sr); st16_bf(gsv + H, sz); st16_bf(gsv + 2 * H, sn); st16_bf(gsv + 3 * H, sg);
-                            }
-                            if (s == T - 1 && c.h_final) {
-                                float* hf = c.h_final + (long long)b * c.h_final_ld + u;
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) hf[j] = hn[j];
-                            }
-                        }
-                    } else {
-                        float dh[16];
-                        if (has_a) tmem_ld_32x16(trow + uu, dh);
-                        else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) dh[j] = 0.f;
-                        }
-                        if (row_ok) {
-                            if (has_a) {
-                                float cr[16];
-                                ld16_cg(c.carry + (long long)b * H + u, cr);
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) dh[j] += cr[j];
-                            }
-                            if (s < 0) {
-                                st16_cg(c.dh0 + (long long)b * H + u, dh);
-                            } else {
-                                const long long row = (long long)s * B + b;
-                                if (c.dhs) add16_bf(c.dhs + row * H + u, dh);
-                                if (s == T - 1 && c.dh_final) add16(c.dh_final + (long long)b * c.dh_final_ld + u, dh);
-                                float r[16], z[16], n[16], ghn[16], hp[16];
-                                const __nv_bfloat16* gsv = c.gates + row * 4 * H + u;
-                                ld16_bf(gsv, r); ld16_bf(gsv + H, z); ld16_bf(gsv + 2 * H, n); ld16_bf(gsv + 3 * H, ghn);
-                                ld16_bf(c.hsx + row * H + u, hp);            // slab s = state before step s
-                                float o_r[16], o_z[16], o_n[16], o_i[16], o_c[16];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const float dnp = dh[j] * (1.f - z[j]) * (1.f - n[j] * n[j]);
-                                    o_z[j] = dh[j] * (hp[j] - n[j]) * z[j] * (1.f - z[j]);
-                                    o_r[j] = dnp * ghn[j] * r[j] * (1.f - r[j]);
-                                    o_n[j] = dnp * r[j];
-                                    o_i[j] = dnp;
-                                    o_c[j] = dh[j] * z[j];
-                                }
-                                __nv_bfloat16* dg = c.dgh + row * 3 * H + u;
-                                st16_bf(dg, o_r); st16_bf(dg + H, o_z); st16_bf(dg + 2 * H, o_n);
-                                st16_bf(c.dgin + row * H + u, o_i);
-                                st16_cg(c.carry + (long long)b * H + u, o_c);
-                            }
-                        }
+                for (int j = 0; j < UT; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; hreg[bt][j] = 0.f; }
+                if (row_ok) {
+                    if (c.proj) {
+                        const float* pj = c.proj + (long long)b * c.proj_ld + u;
+                        ldf<UT>(pj, pr); ldf<UT>(pj + H, pz); ldf<UT>(pj + 2 * H, pn);
                     }
+                    uint32_t hw[UT / 2];
+                    ldb_raw<UT>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
+                    unpack<UT>(hw, hreg[bt]);
                 }
-                if (has_a) {
+#pragma unroll
+                for (int j = 0; j < UT; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[U + uu + j]; }
+                const uint32_t tp = tmem_base + lane_sel + kAccCols + (uint32_t)(bt * N);
+                tmem_st<UT>(tp + uu, pr); tmem_st<UT>(tp + U + uu, pz); tmem_st<UT>(tp + 2 * U + uu, pn);
+            }
+            tmem_st_wait();
+
+            int id_next[NBT];
+#pragma unroll
+            for (int bt = 0; bt < NBT; ++bt) {
+                const int b = bt * 128 + q * 32 + lane;
+                id_next[bt] = (c.emb && b < B) ? c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b] : 0;
+            }
+            for (int s = 0; s < T; ++s) {
+                const int tau = c.reverse ? T - 1 - s : s;
+                const int tau_n = c.reverse ? tau - 1 : tau + 1;
+#pragma unroll
+                for (int bt = 0; bt < NBT; ++bt) {
+                    const int b = bt * 128 + q * 32 + lane;
+                    const bool row_ok = b < B;
+                    const long long row_in = (long long)tau * B + b;       // input side is indexed by time
+                    // ---- operands that do not depend on the recurrence: fetch before waiting for the MMA
+                    float er[UT], ez[UT], en[UT];
+                    uint32_t dr[UT / 2], dz[UT / 2], dn[UT / 2];
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) { er[j] = 0.f; ez[j] = 0.f; en[j] = 0.f; }
+                    if (row_ok && c.emb) {
+                        const float* e = c.emb + (long long)id_next[bt] * 3 * H + u;
+                        ldf<UT>(e, er); ldf<UT>(e + H, ez); ldf<UT>(e + 2 * H, en);
+                        if (s + 1 < T) id_next[bt] = c.ids[(long long)tau_n * B + b];
+                    }
+                    if (row_ok && c.dense) {
+                        const __nv_bfloat16* dp = c.dense + row_in * 3 * H + u;
+                        ldb_raw<UT>(dp, dr, false); ldb_raw<UT>(dp + H, dz, false); ldb_raw<UT>(dp + 2 * H, dn, false);
+                    }
+                    tc::mbar_wait(&sm.acc_full[bt], s & 1);
+                    tc::tc_fence_after();
+                    const uint32_t ta = tmem_base + lane_sel + (uint32_t)(bt * N) + uu;
+                    const uint32_t tp = ta + kAccCols;
+                    float a[UT], p[UT], r[UT], z[UT], n[UT], g[UT];
+                    tmem_ld<UT>(ta, a); tmem_ld<UT>(tp, p);
+                    if (c.dense) { float t[UT]; unpack<UT>(dr, t);
+#pragma unroll
+                        for (int j = 0; j < UT; ++j) er[j] += t[j]; }
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) r[j] = fast_sigmoid(a[j] + p[j] + er[j]);
+                    tmem_ld<UT>(ta + U, a); tmem_ld<UT>(tp + U, p);
+                    if (c.dense) { float t[UT]; unpack<UT>(dz, t);
+#pragma unroll
+                        for (int j = 0; j < UT; ++j) ez[j] += t[j]; }
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) z[j] = fast_sigmoid(a[j] + p[j] + ez[j]);
+                    tmem_ld<UT>(ta + 2 * U, a); tmem_ld<UT>(tp + 2 * U, p);
+                    // accumulator consumed: the tensor core may start the next step of this tile
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&acc_empty[bt]);
+                    if (lane == 0) tc::mbar_arrive(&sm.acc_empty[bt]);
+                    if (c.dense) { float t[UT]; unpack<UT>(dn, t);
+#pragma unroll
+                        for (int j = 0; j < UT; ++j) en[j] += t[j]; }
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) {
+                        g[j] = a[j] + sm.bias[2 * U + uu + j];
+                        n[j] = fast_tanh(p[j] + en[j] + r[j] * g[j]);
+                        hreg[bt][j] = (1.f - z[j]) * n[j] + z[j] * hreg[bt][j];
+                    }
+                    if (row_ok) {
+                        stb<UT>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hreg[bt]);
+                        if (c.gates) {
+                            __nv_bfloat16* gsv = c.gates + row_in * 4 * H + u;
+                            stb<UT>(gsv, r); stb<UT>(gsv + H, z); stb<UT>(gsv + 2 * H, n); stb<UT>(gsv + 3 * H, g);
+                        }
+                        if (s == T - 1 && c.h_final) {          // caller-chosen offset / pitch: no alignment assumed
+                            float* hf = c.h_final + (long long)b * c.h_final_ld + u;
+#pragma unroll
+                            for (int j = 0; j < UT; ++j) hf[j] = hreg[bt][j];
+                        }
+                    }
+                    if (s + 1 < T) publish(gbar + bt);
                 }
             }
-            if (has_a) ++uses;
-            // publish this step to the other slices of the chain
-            if (i + 1 < n_iters) {
-                epi_barrier();
-                if (threadIdx.x == 64) {
-                    __threadfence();
-                    fn_red_release(gbar, 1u);
+        } else {
+            float carry[NBT][UT];
+#pragma unroll
+            for (int bt = 0; bt < NBT; ++bt)
+#pragma unroll
+                for (int j = 0; j < UT; ++j) carry[bt][j] = 0.f;
+            for (int i = 0; i <= T; ++i) {
+                const int s = T - 1 - i;
+                const int tau = c.reverse ? T - 1 - s : s;
+#pragma unroll
+                for (int bt = 0; bt < NBT; ++bt) {
+                    const int b = bt * 128 + q * 32 + lane;
+                    const bool row_ok = b < B;
+                    const long long row = (long long)tau * B + b;
+                    // ---- saved forward values and incoming gradients: fetch before waiting for the MMA
+                    uint32_t wr[UT / 2], wz[UT / 2], wn[UT / 2], wg[UT / 2], wh[UT / 2];
+                    float din[UT];
+#pragma unroll
+                    for (int j = 0; j < UT / 2; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) din[j] = 0.f;
+                    if (row_ok && s >= 0) {
+                        const __nv_bfloat16* gsv = c.gates + row * 4 * H + u;
+                        ldb_raw<UT>(gsv, wr, false); ldb_raw<UT>(gsv + H, wz, false);
+                        ldb_raw<UT>(gsv + 2 * H, wn, false); ldb_raw<UT>(gsv + 3 * H, wg, false);
+                        ldb_raw<UT>(c.hsx + (row + (c.reverse ? B : 0)) * H + u, wh, false);   // the state before step s
+                        if (c.dhs) {
+                            if (c.dhs_f32) ldf<UT>(reinterpret_cast<const float*>(c.dhs) + row * H + u, din);
+                            else {
+                                uint32_t wd[UT / 2];
+                                ldb_raw<UT>(reinterpret_cast<const __nv_bfloat16*>(c.dhs) + row * H + u, wd, false);
+                                unpack<UT>(wd, din);
+                            }
+                        }
+                        if (s == T - 1 && c.dh_final) {
+                            const float* df = c.dh_final + (long long)b * c.dh_final_ld + u;
+#pragma unroll
+                            for (int j = 0; j < UT; ++j) din[j] += __ldg(df + j);
+                        }
+                    }
+                    float dh[UT];
+                    if (i > 0) {
+                        tc::mbar_wait(&sm.acc_full[bt], (i - 1) & 1);
+                        tc::tc_fence_after();
+                        tmem_ld<UT>(tmem_base + lane_sel + (uint32_t)(bt * N) + uu, dh);
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&sm.acc_empty[bt]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < UT; ++j) dh[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) dh[j] += carry[bt][j] + din[j];
+                    if (s < 0) {
+                        if (row_ok) stf<UT>(c.dh0 + (long long)b * H + u, dh);
+                        continue;
+                    }
+                    float r[UT], z[UT], n[UT], g[UT], hp[UT], o_r[UT], o_z[UT], o_n[UT], o_i[UT];
+                    unpack<UT>(wr, r); unpack<UT>(wz, z); unpack<UT>(wn, n); unpack<UT>(wg, g); unpack<UT>(wh, hp);
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) {
+                        const float dnp = dh[j] * (1.f - z[j]) * (1.f - n[j] * n[j]);
+                        o_z[j] = dh[j] * (hp[j] - n[j]) * z[j] * (1.f - z[j]);
+                        o_r[j] = dnp * g[j] * r[j] * (1.f - r[j]);
+                        o_n[j] = dnp * r[j];
+                        o_i[j] = dnp;
+                        carry[bt][j] = dh[j] * z[j];
+                    }
+                    if (row_ok) {
+                        __nv_bfloat16* dgp = c.dg + row * 4 * H + u;
+                        stb<UT>(dgp, o_r); stb<UT>(dgp + H, o_z); stb<UT>(dgp + 2 * H, o_i); stb<UT>(dgp + 3 * H, o_n);
+                    }
+                    publish(gbar + bt);
                 }
             }
         }
@@ -346,22 +478,28 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, 512);
+        tc::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
-size_t tc_smem_bytes(int U, int H, bool bwd) {
-    const int N = bwd ? U : 3 * U, K = bwd ? 3 * H : H;
-    return (size_t)(K / 64) * N * 128 + kAStages * kATile + 1024 /*align*/ + 512 /*barriers*/ + 3 * U * 4;
+// ---- host -------------------------------------------------------------------------------------------
+constexpr size_t kSmemTail = 1024 /*align*/ + 512 /*barriers*/ + 3 * 64 * 4 /*bias*/;
+
+size_t tc_w_bytes(int U, int H, bool bwd) { return (size_t)((bwd ? 3 * H : H) / 64) * (bwd ? U : 3 * U) * 128; }
+int tc_stages(int U, int H, bool bwd) {
+    const long long room = (long long)fn_max_smem_optin() - (long long)tc_w_bytes(U, H, bwd) - (long long)kSmemTail;
+    long long s = room / kATile;
+    if (s > kMaxStages) s = kMaxStages;
+    return (int)s;
 }
 
 int fn_make_tmap_bf16_3d(CUtensorMap* out, const void* base, unsigned long long d2, unsigned long long d1,
-                         unsigned long long d0, unsigned box1, unsigned box0) {
+                         unsigned long long d0, unsigned long long ld1, unsigned box1, unsigned box0) {
     fn_PFN_encodeTiled enc = fn_get_encode_tiled();
     FN_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
-    FN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (d0 * 2) % 16 == 0, "TMA 3-D operand alignment");
+    FN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld1 * 2) % 16 == 0, "TMA 3-D operand alignment");
     cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint64_t strides[2] = {ld1 * 2, ld1 * d1 * 2};
     cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -371,75 +509,83 @@ int fn_make_tmap_bf16_3d(CUtensorMap* out, const void* base, unsigned long long 
     return FN_OK;
 }
 
-int pick_u_tc(int n_chains, int H, int B) {
+// U for a launch of n_chains chains: the widest slice (least re-streaming of the state slab per FLOP)
+// that still leaves >= 2 ring stages and fits the grid on the machine.
+int pick_u_tc(int n_chains, int H, bool bwd) {
     const int sms = fn_num_sms();
-    const size_t cap = (size_t)fn_max_smem_optin();
-    for (int U : {16, 32, 64}) {
+    for (int U : {32, 16}) {
         if (H % U) continue;
-        if (tc_smem_bytes(U, H, false) > cap || tc_smem_bytes(U, H, true) > cap) break;
-        const int nbt = (B + 127) / 128;
-        if (nbt * 3 * U > 512 || nbt > kMaxAcc) break;
-        if ((long long)n_chains * (H / U) <= sms) return U;
+        if (tc_stages(U, H, false) < 2 || tc_stages(U, H, true) < 2) continue;
+        if ((long long)n_chains * (H / U) > sms) continue;
+        return U;
     }
+    (void)bwd;
     return 0;
 }
 
-template <int U, bool BWD>
+template <int U, int NBT, bool BWD>
 int launch_tc(const TcLaunch& P, cudaStream_t st) {
-    const size_t smem = tc_smem_bytes(U, P.H, BWD);
-    const void* fn = (const void*)gru_tc_kernel<U, BWD>;
+    const size_t smem = tc_w_bytes(U, P.H, BWD) + (size_t)P.stages * kATile + kSmemTail;
+    const void* fn = (const void*)gru_tc_kernel<U, NBT, BWD>;
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&P};
     FN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(P.n_chains * P.nslices), dim3(kThreadsTc), args, smem, st));
     return FN_OK;
+}
+template <bool BWD>
+int dispatch_tc(int U, int nbt, const TcLaunch& P, cudaStream_t st) {
+    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD>(P, st) : launch_tc<32, 2, BWD>(P, st);
+    return nbt == 1 ? launch_tc<16, 1, BWD>(P, st) : launch_tc<16, 2, BWD>(P, st);
 }
 
 int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
            cudaStream_t st) {
     FN_REQUIRE(chains && n_chains > 0, "fn_gru_seq_bf16: no chains");
     FN_REQUIRE(B > 0 && T > 0 && H >= 64 && H % 64 == 0, "fn_gru_seq_bf16: need H %% 64 == 0 (H=%d)", H);
+    FN_REQUIRE(B <= 128 * kMaxNbt, "fn_gru_seq_bf16: B=%d > %d rows per chain (split the batch into several chains)", B,
+               128 * kMaxNbt);
     FN_REQUIRE(barrier_ws && ws_bytes >= (size_t)64 * n_chains, "fn_gru_seq_bf16: barrier_ws too small");
     FN_CHECK_CUDA(cudaMemsetAsync(barrier_ws, 0, (size_t)64 * n_chains, st));
+    const int nbt = (B + 127) / 128;
     int done = 0;
     while (done < n_chains) {
         int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc, U = 0;
         for (; group >= 1; --group)
-            if ((U = pick_u_tc(group, H, B)) != 0) break;
-        FN_REQUIRE(group >= 1, "fn_gru_seq_bf16: shape H=%d B=%d not supported by the tcgen05 path", H, B);
+            if ((U = pick_u_tc(group, H, bwd)) != 0) break;
+        FN_REQUIRE(group >= 1, "fn_gru_seq_bf16: H=%d not supported by the tcgen05 path", H);
         TcLaunch P;
         memset(&P, 0, sizeof(P));
         for (int i = 0; i < group; ++i) {
             const FnGruChainBf16& s = chains[done + i];
             TcChain& d = P.c[i];
             int rc;
+            FN_REQUIRE(s.hsx, "fn_gru_seq_bf16: chain %d misses hsx", done + i);
             if (!bwd) {
-                FN_REQUIRE(s.w_hh && s.b_hh && s.hsx && s.hcur, "fn_gru_seq_fwd_bf16: chain %d misses buffers", done + i);
+                FN_REQUIRE(s.w_hh && s.b_hh, "fn_gru_seq_fwd_bf16: chain %d misses weights", done + i);
                 FN_REQUIRE(!s.emb || s.ids, "fn_gru_seq_fwd_bf16: chain %d has emb without ids", done + i);
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh, 3ull * H, H, H, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, H, 128, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, H, H, 128, 64);
                 if (rc) return rc;
             } else {
-                FN_REQUIRE(s.w_hh_t && s.hsx && s.gates && s.dgh && s.dgin && s.dh0 && s.carry,
-                           "fn_gru_seq_bwd_bf16: chain %d misses buffers", done + i);
+                FN_REQUIRE(s.w_hh_t && s.gates && s.dg && s.dh0, "fn_gru_seq_bwd_bf16: chain %d misses buffers", done + i);
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh_t, H, 3ull * H, 3ull * H, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dgh, T, B, 3ull * H, 128, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, 4ull * H, 4ull * H, 128, 64);
                 if (rc) return rc;
             }
             d.b_hh = s.b_hh; d.emb = s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
-            d.dense = (const __nv_bfloat16*)s.dense; d.h0 = s.h0;
-            d.hsx = (__nv_bfloat16*)s.hsx; d.hcur = s.hcur; d.gates = (__nv_bfloat16*)s.gates;
+            d.dense = (const __nv_bfloat16*)s.dense;
+            d.hsx = (__nv_bfloat16*)s.hsx; d.gates = (__nv_bfloat16*)s.gates;
             d.h_final = s.h_final; d.h_final_ld = s.h_final_ld;
-            d.dhs = (const __nv_bfloat16*)s.dhs; d.dh_final = s.dh_final; d.dh_final_ld = s.dh_final_ld;
-            d.dgh = (__nv_bfloat16*)s.dgh; d.dgin = (__nv_bfloat16*)s.dgin; d.dh0 = s.dh0; d.carry = s.carry;
+            d.dhs = s.dhs; d.dh_final = s.dh_final; d.dh_final_ld = s.dh_final_ld;
+            d.dg = (__nv_bfloat16*)s.dg; d.dh0 = s.dh0;
+            d.reverse = s.reverse; d.dhs_f32 = s.dhs_f32;
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
         P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H;
-        int rc;
-        if (U == 16) rc = bwd ? launch_tc<16, true>(P, st) : launch_tc<16, false>(P, st);
-        else if (U == 32) rc = bwd ? launch_tc<32, true>(P, st) : launch_tc<32, false>(P, st);
-        else rc = bwd ? launch_tc<64, true>(P, st) : launch_tc<64, false>(P, st);
+        P.stages = tc_stages(U, H, bwd);
+        const int rc = bwd ? dispatch_tc<true>(U, nbt, P, st) : dispatch_tc<false>(U, nbt, P, st);
         if (rc != FN_OK) return rc;
         done += group;
     }

@@ -29,6 +29,18 @@ class FnGruChain(C.Structure):
     ]
 
 
+class FnGruChainBf16(C.Structure):
+    """Mirror of `struct FnGruChainBf16` (include/fadernets_b200.h)."""
+    _fields_ = [
+        ("w_hh", C.c_void_p), ("w_hh_t", C.c_void_p), ("b_hh", C.c_void_p),
+        ("emb", C.c_void_p), ("ids", C.c_void_p), ("proj", C.c_void_p), ("proj_ld", c_ll),
+        ("dense", C.c_void_p), ("reverse", C.c_int32), ("dhs_f32", C.c_int32),
+        ("hsx", C.c_void_p), ("gates", C.c_void_p), ("h_final", C.c_void_p), ("h_final_ld", c_ll),
+        ("dhs", C.c_void_p), ("dh_final", C.c_void_p), ("dh_final_ld", c_ll),
+        ("dg", C.c_void_p), ("dh0", C.c_void_p),
+    ]
+
+
 V, I, LL, F, SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); int-returning functions are status codes and are checked.
@@ -41,6 +53,13 @@ _SIGNATURES = {
     "fn_gru_seq_fwd_f32": (I, [C.POINTER(FnGruChain), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_bwd_f32": (I, [C.POINTER(FnGruChain), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_ctas_per_chain": (I, [I]),
+    "fn_gru_seq_fwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
+    "fn_gru_seq_bwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
+    "fn_cast_bf16": (I, [V, LL, LL, V, LL, LL, LL, V]),
+    "fn_ids_to_onehot_bf16": (I, [V, LL, I, LL, V, V]),
+    "fn_time_sum_bf16": (I, [V, I, I, I, V, V, V]),
+    "fn_col_sum_bf16": (I, [V, LL, LL, I, V, I, V, SZ, V]),
+    "fn_add_f32_to_bf16": (I, [V, V, LL, V]),
     "fn_onehot_to_ids": (I, [V, I, I, I, V, V]),
     "fn_ids_to_onehot": (I, [V, I, I, I, V, V]),
     "fn_ids_to_time_major": (I, [V, I, I, I, I, V, V]),

@@ -19,6 +19,9 @@ from torch.distributions import Normal
 from . import ops
 from ._lib import FaderNetsError, require_cuda
 from .ops import ChainSpec, GruGroupFn, LatentHeadFn, QyXFn, TimeLogSoftmaxFn, VocabLogSoftmaxFn, linear
+from .ops_bf16 import GruGroupBf16Fn, linear_bf16
+
+PRECISIONS = ("f32", "bf16")
 
 START_TOKEN_FROM_END = 1          # decoder start symbol = one-hot of the LAST vocabulary index (gmm_model.py:120-121)
 CDTL_DIMS = 24                    # chroma conditioning width hard-coded by the reference (gmm_model.py:53)
@@ -58,6 +61,7 @@ class _FaderBase(nn.Module):
         self._flat = None
         self._flat_grad = None
         self.host_rng = True          # draw eps exactly like the reference (CPU default generator)
+        self.precision = "f32"        # "f32": exact-parity SIMT path; "bf16": tcgen05 tensor-core path
 
     # ---------------------------------------------------------------- flat parameter storage
     def live_parameters(self):
@@ -100,6 +104,24 @@ class _FaderBase(nn.Module):
             if p.grad is None or p.grad.data_ptr() != grad.data_ptr() + off * 4:
                 p.grad = grad[off:off + n].view(p.shape)
             off += ((n + 3) // 4) * 4
+
+    def set_precision(self, precision: str):
+        """"f32" (default): every product in fp32 FMA -- the 1e-3 parity mode.  "bf16": the T-scale products
+        (GRU gate block, vocabulary / attribute heads, their gradients) on the tcgen05 tensor cores with bf16
+        operands and fp32 accumulation (BASELINE configs 3-5); parameters and reductions stay fp32."""
+        if precision not in PRECISIONS:
+            raise FaderNetsError(f"precision must be one of {PRECISIONS}")
+        self.precision = precision
+        return self
+
+    def _gru(self):
+        return GruGroupBf16Fn if self.precision == "bf16" else GruGroupFn
+
+    def _tlinear(self, x, lin):
+        """Linear over a T*B-row activation (time-major hidden states)."""
+        if self.precision == "bf16":
+            return linear_bf16(x, lin.weight, lin.bias)
+        return linear(x, lin.weight, lin.bias)
 
     # ---------------------------------------------------------------- helpers
     def _check_device(self):
@@ -151,7 +173,7 @@ class _FaderBase(nn.Module):
                 specs.append(ChainSpec(emb_cols=(0, V), ids=ids_tm, reverse=rev, final=(gi, H if rev else 0)))
                 tensors += [getattr(g, f"weight_ih_l0{sfx}"), getattr(g, f"bias_ih_l0{sfx}"),
                             getattr(g, f"weight_hh_l0{sfx}"), getattr(g, f"bias_hh_l0{sfx}")]
-        hcat_r, hcat_n = GruGroupFn.apply(specs, B, T, H, (2 * H, 2 * H), *tensors)
+        hcat_r, hcat_n = self._gru().apply(specs, B, T, H, (2 * H, 2 * H), *tensors)
         mu_r, pre_r = linear(hcat_r, self.mu_r.weight, self.mu_r.bias), linear(hcat_r, self.var_r.weight, self.var_r.bias)
         mu_n, pre_n = linear(hcat_n, self.mu_n.weight, self.mu_n.bias), linear(hcat_n, self.var_n.weight, self.var_n.bias)
         return mu_r, pre_r, mu_n, pre_n
@@ -190,20 +212,20 @@ class _FaderBase(nn.Module):
             tensors += [c.weight_ih, c.bias_ih, c.weight_hh, c.bias_hh, zc,
                         linear(zc, self.linear_init_global.weight, self.linear_init_global.bias)]
             names.append("g")
-        hs = dict(zip(names, GruGroupFn.apply(specs, B, T, H, (), *tensors)))
+        hs = dict(zip(names, self._gru().apply(specs, B, T, H, (), *tensors)))
         if "g" in hs:
             c2 = self.grucell_g_2
-            (hs["g2"],) = GruGroupFn.apply([ChainSpec(x_cols=(0, H), h0="xin0", want_hs=True)], B, T, H, (),
-                                           c2.weight_ih, c2.bias_ih, c2.weight_hh, c2.bias_hh, hs["g"])
+            (hs["g2"],) = self._gru().apply([ChainSpec(x_cols=(0, H), h0="xin0", want_hs=True)], B, T, H, (),
+                                            c2.weight_ih, c2.bias_ih, c2.weight_hh, c2.bias_hh, hs["g"])
         return hs
 
     def _sub_decoder_outputs(self, hs):
-        lr = linear(hs["r"], self.linear_out_r.weight, self.linear_out_r.bias)
-        ln = linear(hs["n"], self.linear_out_n.weight, self.linear_out_n.bias)
+        lr = self._tlinear(hs["r"], self.linear_out_r)
+        ln = self._tlinear(hs["n"], self.linear_out_n)
         return TimeLogSoftmaxFn.apply(lr), TimeLogSoftmaxFn.apply(ln)
 
     def _global_logits(self, hs):
-        return linear(hs["g2"], self.linear_out_g.weight, self.linear_out_g.bias)       # [T,B,V]
+        return self._tlinear(hs["g2"], self.linear_out_g)       # [T,B,V]
 
     def sub_decoders(self, rhythm, z_r, note, z_n):
         """gmm_model.py:100-117 / model_v2.py:99-116 (log-softmax over the time axis)."""

@@ -1,0 +1,288 @@
+"""autograd glue of the bf16 tensor-core path (tcgen05): the persistent GRU gate block
+(fn_gru_seq_*_bf16) and every batched product (fn_tc_gemm_bf16).
+
+Same graph as fadernets_b200.ops (the fp32 exact-parity path); what changes is the storage of the
+T-scale activations -- hidden states, saved gates and gate gradients are bf16, time-major, with the
+initial state as an extra slab -- and that every product with a T*B-row operand runs on the tensor
+cores with fp32 accumulation.  Parameters, their gradients, the latent block and all reductions stay
+fp32.  torch only allocates; no torch operator does arithmetic here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+
+from ._lib import LIB, FnGruChainBf16, require_cuda, stream_ptr
+from .ops import F32, ChainSpec, _f32c, _p, _st, col_sum, gemm
+
+BF16 = torch.bfloat16
+
+
+def r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def cast_bf16(src: torch.Tensor, rows: int, cols: int, s_r: int, s_c: int, off: int = 0, ld_dst: int | None = None):
+    """bf16 copy of the fp32 matrix view src[off + r*s_r + c*s_c] -> [rows][ld_dst]."""
+    ld = cols if ld_dst is None else ld_dst
+    dst = torch.empty((rows, ld), dtype=BF16, device=src.device)
+    LIB.call("fn_cast_bf16", _p(src, off), s_r, s_c, _p(dst), ld, rows, cols, _st(dst))
+    return dst
+
+
+def to_bf16_rows(x: torch.Tensor, cols: int):
+    """x: [..., cols] fp32 or bf16 -> (bf16 2-D [rows][ld], ld) with ld % 8 == 0 (TMA row pitch)."""
+    rows = x.numel() // cols
+    if x.dtype == BF16 and cols % 8 == 0 and x.is_contiguous():
+        return x.view(rows, cols), cols
+    xf = _f32c(x)
+    ld = r8(cols)
+    return cast_bf16(xf, rows, cols, cols, 1, ld_dst=ld), ld
+
+
+def tc_gemm(A, a_off, lda, a_mn, B, b_off, ldb, b_mn, Cm, c_off, ldc, bias, M, N, K, accumulate=False):
+    """C[M][N] (fp32 or bf16 by Cm.dtype) (+)= A * B (+ bias); operand layouts as in fn_tc_gemm_bf16."""
+    LIB.call("fn_tc_gemm_bf16", _p(A, a_off), lda, a_mn, _p(B, b_off), ldb, b_mn, _p(Cm, c_off), ldc,
+             1 if Cm.dtype == BF16 else 0, _p(bias), M, N, K, 1 if accumulate else 0, _st(Cm))
+
+
+def col_sum_bf16(x, ld, rows, cols, out, accumulate=False):
+    scratch = torch.empty(64 * cols * 4, dtype=torch.uint8, device=x.device)
+    LIB.call("fn_col_sum_bf16", _p(x), ld, rows, cols, _p(out), 1 if accumulate else 0, _p(scratch), scratch.numel(),
+             _st(x))
+
+
+def onehot_bf16(ids_tm: torch.Tensor, V: int):
+    """int32 ids [rows...] -> bf16 one-hot [rows][r8(V)]."""
+    rows = ids_tm.numel()
+    ld = r8(V)
+    out = torch.empty((rows, ld), dtype=BF16, device=ids_tm.device)
+    LIB.call("fn_ids_to_onehot_bf16", _p(ids_tm), rows, V, ld, _p(out), _st(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear on the tensor cores
+# ------------------------------------------------------------------------------------------------
+class LinearBf16Fn(torch.autograd.Function):
+    """y = x W^T + b with x [..., K] (bf16 or fp32; K % 8 == 0), W [N,K] fp32 master weights.
+    y is fp32 unless out_bf16.  dx is returned in x's dtype; dW, db fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, out_bf16=False):
+        require_cuda(x, w)
+        K = x.shape[-1]
+        M = x.numel() // K
+        N = w.shape[0]
+        xb, ldx = to_bf16_rows(x, K)
+        wb = cast_bf16(w, N, K, K, 1, ld_dst=r8(K))
+        y = torch.empty(x.shape[:-1] + (N,), dtype=BF16 if out_bf16 else F32, device=x.device)
+        tc_gemm(xb, 0, ldx, 0, wb, 0, r8(K), 0, y, 0, N, b, M, N, K)
+        ctx.save_for_backward(xb, wb)
+        ctx.meta = (M, N, K, ldx, x.dtype, x.shape, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        M, N, K, ldx, xdtype, xshape, has_bias = ctx.meta
+        dev = xb.device
+        dyb, ldy = to_bf16_rows(dy, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(xshape, dtype=xdtype, device=dev)
+            tc_gemm(dyb, 0, ldy, 0, wb, 0, r8(K), 1, dx, 0, K, None, M, K, N)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((N, K), dtype=F32, device=dev)
+            tc_gemm(dyb, 0, ldy, 1, xb, 0, ldx, 1, dw, 0, K, None, N, K, M)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(N, dtype=F32, device=dev)
+            col_sum_bf16(dyb, ldy, M, N, db)
+        return dx, dw, db, None
+
+
+def linear_bf16(x, w, b, out_bf16=False):
+    return LinearBf16Fn.apply(x, w, b, out_bf16)
+
+
+# ------------------------------------------------------------------------------------------------
+# GRU chains on the tensor cores
+# ------------------------------------------------------------------------------------------------
+class GruGroupBf16Fn(torch.autograd.Function):
+    """Same contract as ops.GruGroupFn (specs, B, T, H, final_widths, *tensors) with bf16 state storage.
+    hs outputs are bf16 [T,B,H] views of the chain's [T+1,B,H] slab buffer; a dense input `xin` (and its
+    `h0 == "xin0"`) is expected in bf16 [T,B,Hin]."""
+
+    @staticmethod
+    def forward(ctx, specs: List[ChainSpec], B: int, T: int, H: int, final_widths, *tensors):
+        dev = tensors[0].device
+        require_cuda(*tensors)
+        need_grad = any(ctx.needs_input_grad)
+        n = len(specs)
+        chains = (FnGruChainBf16 * n)()
+        finals = [torch.empty((B, wd), dtype=F32, device=dev) for wd in final_widths]
+        keep, tmp = [], []
+        pos = 0
+        K3 = 3 * H
+        for ci, sp in enumerate(specs):
+            w_ih, b_ih, w_hh, b_hh = tensors[pos:pos + 4]
+            pos += 4
+            z_in = xin = h0 = None
+            if sp.z_cols is not None:
+                z_in = _f32c(tensors[pos]); pos += 1
+            if sp.x_cols is not None:
+                xin = tensors[pos]; pos += 1
+                assert xin.dtype == BF16 and xin.is_contiguous(), "bf16 GRU path: dense input must be contiguous bf16"
+            if sp.h0 == "tensor":
+                h0 = _f32c(tensors[pos]); pos += 1
+            In = w_ih.shape[1]
+            ch = chains[ci]
+            d = dict(w_ih=w_ih, w_hh=w_hh, z_in=z_in, xin=xin, spec=sp)
+            whb = cast_bf16(w_hh, K3, H, H, 1)
+            d["w_hh_b"] = whb
+            ch.w_hh, ch.b_hh = whb.data_ptr(), b_hh.data_ptr()
+            if sp.emb_cols is not None:
+                c0, Vin = sp.emb_cols
+                emb = torch.empty((Vin, K3), dtype=F32, device=dev)
+                LIB.call("fn_transpose_f32", _p(w_ih, c0), In, _p(emb), K3, K3, Vin, 0, _st(emb))
+                ch.emb, ch.ids = emb.data_ptr(), sp.ids.data_ptr()
+                tmp.append(emb)
+            if sp.z_cols is not None:
+                c0, Zin = sp.z_cols
+                proj = torch.empty((B, K3), dtype=F32, device=dev)
+                gemm(z_in, 0, Zin, 1, w_ih, c0, 1, In, proj, 0, K3, b_ih, B, K3, Zin)
+                ch.proj, ch.proj_ld = proj.data_ptr(), K3
+                tmp.append(proj)
+            elif sp.x_cols is None:
+                ch.proj, ch.proj_ld = b_ih.data_ptr(), 0
+            if sp.x_cols is not None:
+                c0, Hin = sp.x_cols
+                wib = cast_bf16(w_ih, K3, In, In, 1, ld_dst=r8(In))
+                d["w_ih_b"] = wib
+                dense = torch.empty((T, B, K3), dtype=BF16, device=dev)
+                tc_gemm(xin, 0, Hin, 0, wib, c0, r8(In), 0, dense, 0, K3, b_ih, T * B, K3, Hin)
+                ch.dense = dense.data_ptr()
+                tmp.append(dense)
+            hsx = torch.empty((T + 1, B, H), dtype=BF16, device=dev)
+            init = hsx[T if sp.reverse else 0]
+            if sp.h0 == "tensor":
+                LIB.call("fn_cast_bf16", _p(h0), H, 1, _p(init), H, B, H, _st(init))
+            elif sp.h0 == "xin0":
+                init.copy_(xin[0])
+            else:
+                init.zero_()
+            ch.hsx = hsx.data_ptr()
+            ch.reverse = 1 if sp.reverse else 0
+            d["hsx"] = hsx
+            if need_grad:
+                gates = torch.empty((T, B, 4 * H), dtype=BF16, device=dev)
+                ch.gates = gates.data_ptr()
+                d["gates"] = gates
+            if sp.final is not None:
+                fi, fc = sp.final
+                ch.h_final = finals[fi].data_ptr() + fc * 4
+                ch.h_final_ld = finals[fi].shape[1]
+            keep.append(d)
+        bar = torch.empty(64 * n, dtype=torch.uint8, device=dev)
+        LIB.call("fn_gru_seq_fwd_bf16", chains, n, B, T, H, _p(bar), bar.numel(), stream_ptr(dev))
+        del tmp
+        ctx.specs, ctx.dims, ctx.keep, ctx.n_finals = specs, (B, T, H), keep, len(finals)
+        outs = list(finals)
+        for i, sp in enumerate(specs):
+            if sp.want_hs:
+                assert not sp.reverse
+                outs.append(keep[i]["hsx"][1:])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        specs, (B, T, H), keep = ctx.specs, ctx.dims, ctx.keep
+        dev = keep[0]["hsx"].device
+        K3, H4, TB = 3 * H, 4 * H, T * B
+        n = len(specs)
+        gfinals = [None if g is None else _f32c(g) for g in grads[:ctx.n_finals]]
+        ghs_iter = iter(grads[ctx.n_finals:])
+        chains = (FnGruChainBf16 * n)()
+        bufs = []
+        for ci, sp in enumerate(specs):
+            d, ch = keep[ci], chains[ci]
+            wht = cast_bf16(d["w_hh"], H, K3, 1, H)                    # W_hh^T [H][3H]
+            ch.w_hh_t = wht.data_ptr()
+            ch.reverse = 1 if sp.reverse else 0
+            ch.hsx, ch.gates = d["hsx"].data_ptr(), d["gates"].data_ptr()
+            dhs = None
+            if sp.want_hs:
+                g = next(ghs_iter)
+                if g is not None:
+                    dhs = g if g.is_contiguous() else g.contiguous()
+                    ch.dhs = dhs.data_ptr()
+                    ch.dhs_f32 = 0 if dhs.dtype == BF16 else 1
+                    if dhs.dtype not in (BF16, F32):
+                        dhs = dhs.float(); ch.dhs = dhs.data_ptr(); ch.dhs_f32 = 1
+            if sp.final is not None and gfinals[sp.final[0]] is not None:
+                gf = gfinals[sp.final[0]]
+                ch.dh_final = gf.data_ptr() + sp.final[1] * 4
+                ch.dh_final_ld = gf.shape[1]
+            b = dict(dg=torch.empty((T, B, H4), dtype=BF16, device=dev), dh0=torch.empty((B, H), dtype=F32, device=dev),
+                     dhs=dhs, wht=wht)
+            ch.dg, ch.dh0 = b["dg"].data_ptr(), b["dh0"].data_ptr()
+            bufs.append(b)
+        bar = torch.empty(64 * n, dtype=torch.uint8, device=dev)
+        st = stream_ptr(dev)
+        LIB.call("fn_gru_seq_bwd_bf16", chains, n, B, T, H, _p(bar), bar.numel(), st)
+
+        out_grads = []
+        for ci, sp in enumerate(specs):
+            d, b = keep[ci], bufs[ci]
+            w_ih, hsx, dg = d["w_ih"], d["hsx"], b["dg"]
+            In = w_ih.shape[1]
+            # ---- recurrent weight: dW_hh = sum_tau dgh_tau^T (state before that step); rows tau*B+b of dg pair
+            # with slab tau (forward chain) / tau+1 (reverse chain) of hsx.  dgh = dg[:, :2H] | dg[:, 3H:].
+            dw_hh = torch.empty((K3, H), dtype=F32, device=dev)
+            hoff = B * H if sp.reverse else 0
+            tc_gemm(dg, 0, H4, 1, hsx, hoff, H, 1, dw_hh, 0, H, None, 2 * H, H, TB)
+            tc_gemm(dg, K3, H4, 1, hsx, hoff, H, 1, dw_hh, 2 * H * H, H, None, H, H, TB)
+            # ---- time sums -> biases and the time-invariant projection
+            dproj = torch.empty((B, K3), dtype=F32, device=dev)
+            dghsum = torch.empty((B, K3), dtype=F32, device=dev)
+            LIB.call("fn_time_sum_bf16", _p(dg), B, T, H, _p(dproj), _p(dghsum), st)
+            db_hh = torch.empty(K3, dtype=F32, device=dev)
+            db_ih = torch.empty(K3, dtype=F32, device=dev)
+            col_sum(dghsum, K3, B, K3, db_hh)
+            col_sum(dproj, K3, B, K3, db_ih)
+            # ---- input weight
+            covered = sum(c[1] for c in (sp.emb_cols, sp.z_cols, sp.x_cols) if c is not None)
+            dw_ih = (torch.empty if covered == In else torch.zeros)((K3, In), dtype=F32, device=dev)
+            dz_in = dxin = None
+            if sp.emb_cols is not None:
+                # autograd of `onehot @ W_ih[:, :Vin]^T`: dW_ih[:, :Vin] = dgi^T onehot, on the tensor cores
+                # (the one-hot operand is exact in bf16)
+                c0, Vin = sp.emb_cols
+                oh = onehot_bf16(sp.ids, Vin)
+                tc_gemm(dg, 0, H4, 1, oh, 0, r8(Vin), 1, dw_ih, c0, In, None, K3, Vin, TB)
+            if sp.z_cols is not None:
+                c0, Zin = sp.z_cols
+                z_in = d["z_in"]
+                gemm(dproj, 0, 1, K3, z_in, 0, Zin, 1, dw_ih, c0, In, None, K3, Zin, B)
+                dz_in = torch.empty((B, Zin), dtype=F32, device=dev)
+                gemm(dproj, 0, K3, 1, w_ih, c0, In, 1, dz_in, 0, Zin, None, B, Zin, K3)
+            if sp.x_cols is not None:
+                c0, Hin = sp.x_cols
+                xin, wib = d["xin"], d["w_ih_b"]
+                dxin = torch.empty((T, B, Hin), dtype=BF16, device=dev)
+                tc_gemm(dg, 0, H4, 0, wib, c0, r8(In), 1, dxin, 0, Hin, None, TB, Hin, K3)
+                tc_gemm(dg, 0, H4, 1, xin, 0, Hin, 1, dw_ih, c0, In, None, K3, Hin, TB)
+                if sp.h0 == "xin0":
+                    # grad wrt xin[0] also receives the initial-state gradient of this chain
+                    LIB.call("fn_add_f32_to_bf16", _p(dxin), _p(b["dh0"]), B * Hin, st)
+            out_grads += [dw_ih, db_ih, dw_hh, db_hh]
+            if sp.z_cols is not None:
+                out_grads.append(dz_in)
+            if sp.x_cols is not None:
+                out_grads.append(dxin)
+            if sp.h0 == "tensor":
+                out_grads.append(b["dh0"])
+        ctx.keep = None
+        return (None, None, None, None, None) + tuple(out_grads)

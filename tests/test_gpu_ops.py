@@ -261,3 +261,141 @@ def test_tc_gemm_bf16(dev, M, N, K, a_mn, b_mn, c_bf16):
     else:
         close(Cm[:, :N], ref[:, :N], rtol=2e-5, atol=1e-4, what="tc gemm (fp32 out)")
     assert torch.equal(Cm[:, N:], Cin[:, N:]), "wrote outside the tile"
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core path
+# ------------------------------------------------------------------------------------------------
+def _ste_bf16(x):
+    """bf16 rounding with a straight-through gradient (what the kernels do to MMA operands)."""
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
+
+def _torch_gru_bf16(gi, h0, w_hh, b_hh, reverse):
+    """_torch_gru with the tensor-core path's operand rounding: bf16 W_hh and bf16 state INTO the product,
+    fp32 (here fp64) everywhere else."""
+    T, B, _ = gi.shape
+    H = w_hh.shape[1]
+    wq = _ste_bf16(w_hh)
+    h = _ste_bf16(h0)                      # the initial-state slab is bf16
+    hs = [None] * T
+    for s in range(T):
+        t = T - 1 - s if reverse else s
+        gh = _ste_bf16(h) @ wq.t() + b_hh
+        r = torch.sigmoid(gi[t, :, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[t, :, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[t, :, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+        hs[t] = h
+    return torch.stack(hs, 0)
+
+
+@pytest.mark.parametrize("B,T,H,Vin,Zin", [(3, 5, 64, 7, 4), (70, 9, 64, 342, 12), (200, 6, 128, 16, 8),
+                                           (130, 4, 256, 3, 8), (256, 3, 512, 342, 24), (5, 1, 64, 3, 8)])
+def test_gru_group_bf16(dev, B, T, H, Vin, Zin):
+    """tcgen05 GRU: three chains in one launch -- (emb, reverse, zero h0, final state) / (emb + z-projection,
+    h0) / (dense bf16 input, h0 = xin[0]) -- forward values and every gradient against a torch fp64
+    restatement with the same bf16 operand rounding.  Tolerances are bf16-level (saved gates and gate
+    gradients are stored in bf16)."""
+    from fadernets_b200.ops import ChainSpec
+    from fadernets_b200.ops_bf16 import GruGroupBf16Fn
+    bf = torch.bfloat16
+    k = 1.0 / math.sqrt(H)
+    def par(*shape, seed):
+        return (rnd(*shape, seed=seed, dev=dev) * k).requires_grad_(True)
+    ids = torch.randint(0, Vin, (T, B), generator=torch.Generator().manual_seed(5)).int().to(dev)
+    wa = [par(3 * H, Vin, seed=10), par(3 * H, seed=11), par(3 * H, H, seed=12), par(3 * H, seed=13)]
+    wb = [par(3 * H, Vin + Zin, seed=20), par(3 * H, seed=21), par(3 * H, H, seed=22), par(3 * H, seed=23)]
+    zin = rnd(B, Zin, seed=24, dev=dev).requires_grad_(True)
+    h0b = rnd(B, H, seed=25, dev=dev).requires_grad_(True)
+    wc = [par(3 * H, H, seed=30), par(3 * H, seed=31), par(3 * H, H, seed=32), par(3 * H, seed=33)]
+    xin = rnd(T, B, H, seed=34, dev=dev, scale=0.5).to(bf).requires_grad_(True)
+    specs = [ChainSpec(emb_cols=(0, Vin), ids=ids, reverse=True, final=(0, 2)),
+             ChainSpec(emb_cols=(0, Vin), ids=ids, z_cols=(Vin, Zin), h0="tensor", want_hs=True),
+             ChainSpec(x_cols=(0, H), h0="xin0", want_hs=True)]
+    fin, hs_b, hs_c = GruGroupBf16Fn.apply(specs, B, T, H, (H + 5,), *wa, *wb, zin, h0b, *wc, xin)
+    assert hs_b.dtype == bf and hs_c.dtype == bf and fin.dtype == torch.float32
+    go_f, go_b, go_c = rnd(B, H, seed=40, dev=dev), rnd(T, B, H, seed=41, dev=dev).to(bf), rnd(T, B, H, seed=42, dev=dev).to(bf)
+    loss = (fin[:, 2:2 + H] * go_f).sum() + (hs_b.float() * go_b.float()).sum() + (hs_c.float() * go_c.float()).sum()
+    leaves = wa + wb + [zin, h0b] + wc + [xin]
+    grads = torch.autograd.grad(loss, leaves)
+    torch.cuda.synchronize()
+
+    D = [t.detach().double().requires_grad_(True) for t in leaves]
+    a_wih, a_bih, a_whh, a_bhh, b_wih, b_bih, b_whh, b_bhh, zin_, h0b_, c_wih, c_bih, c_whh, c_bhh, xin_ = D
+    idl = ids.long()
+    gi_a = a_wih.t()[idl] + a_bih
+    ra = _torch_gru_bf16(gi_a, torch.zeros(B, H, dtype=torch.float64, device=dev), a_whh, a_bhh, True)
+    gi_b = b_wih[:, :Vin].t()[idl] + (zin_ @ b_wih[:, Vin:].t() + b_bih)[None]
+    rb = _torch_gru_bf16(gi_b, h0b_, b_whh, b_bhh, False)
+    gi_c = _ste_bf16(xin_ @ _ste_bf16(c_wih).t() + c_bih)          # the dense stream is stored in bf16
+    rc = _torch_gru_bf16(gi_c, xin_[0], c_whh, c_bhh, False)
+    close(fin[:, 2:2 + H], ra[0], rtol=2e-3, atol=2e-3, what="final state (reverse chain)")
+    close(hs_b.float(), rb, rtol=1e-2, atol=5e-3, what="hs chain B")
+    close(hs_c.float(), rc, rtol=1e-2, atol=5e-3, what="hs chain C")
+    rloss = (ra[0] * go_f.double()).sum() + (rb * go_b.double()).sum() + (rc * go_c.double()).sum()
+    rgrads = torch.autograd.grad(rloss, D)
+    names = ["a_wih", "a_bih", "a_whh", "a_bhh", "b_wih", "b_bih", "b_whh", "b_bhh", "zin", "h0b", "c_wih", "c_bih",
+             "c_whh", "c_bhh", "xin"]
+    for nm, g, rg in zip(names, grads, rgrads):
+        close(g.float(), rg, rtol=3e-2, atol=1e-3, what="grad " + nm)
+
+
+def test_bf16_aux_kernels(dev):
+    from fadernets_b200._lib import LIB
+    from fadernets_b200.ops import _p, _st
+    from fadernets_b200 import ops_bf16 as ob
+    bf = torch.bfloat16
+    # casts (contiguous, padded pitch, transposing)
+    x = rnd(37, 50, seed=1, dev=dev)
+    assert torch.equal(ob.cast_bf16(x, 37, 50, 50, 1), x.to(bf))
+    p = ob.cast_bf16(x, 37, 50, 50, 1, ld_dst=56)
+    assert torch.equal(p[:, :50], x.to(bf))
+    assert torch.equal(ob.cast_bf16(x, 50, 37, 1, 50), x.t().to(bf))
+    y = rnd(64, 128, seed=2, dev=dev)
+    assert torch.equal(ob.cast_bf16(y, 64, 128, 128, 1), y.to(bf))
+    # one-hot operand
+    ids = torch.randint(0, 342, (1000,), generator=torch.Generator().manual_seed(3)).int().to(dev)
+    oh = ob.onehot_bf16(ids, 342)
+    assert oh.shape == (1000, 344)
+    assert torch.equal(oh[:, :342].float(), torch.nn.functional.one_hot(ids.long(), 342).float()) and float(oh[:, 342:].abs().sum()) == 0
+    oh3 = ob.onehot_bf16(ids % 3, 3)
+    assert torch.equal(oh3[:, :3].float(), torch.nn.functional.one_hot((ids % 3).long(), 3).float())
+    # time sums over dg [T][B][4H]
+    T, B, H = 7, 5, 16
+    dg = rnd(T, B, 4 * H, seed=4, dev=dev).to(bf)
+    dproj = torch.empty(B, 3 * H, device=dev); dgh = torch.empty(B, 3 * H, device=dev)
+    LIB.call("fn_time_sum_bf16", _p(dg), B, T, H, _p(dproj), _p(dgh), _st(dg))
+    s = dg.float().sum(0)
+    close(dproj, s[:, :3 * H], what="time sum dproj")
+    close(dgh, torch.cat([s[:, :2 * H], s[:, 3 * H:]], 1), what="time sum dgh")
+    # column sum
+    xb = rnd(1000, 24, seed=5, dev=dev).to(bf)
+    out = torch.ones(19, device=dev)
+    ob.col_sum_bf16(xb, 24, 1000, 19, out, accumulate=True)
+    close(out, xb.float()[:, :19].sum(0) + 1, rtol=1e-5, atol=1e-4, what="col sum bf16")
+    # bf16 += fp32
+    a = rnd(100, seed=6, dev=dev).to(bf); b = rnd(100, seed=7, dev=dev)
+    a0 = a.clone()
+    LIB.call("fn_add_f32_to_bf16", _p(a), _p(b), 100, _st(a))
+    assert torch.equal(a, (a0.float() + b).to(bf))
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 342, 64), (1000, 3, 128), (257, 16, 256)])
+def test_linear_bf16(dev, M, N, K):
+    from fadernets_b200.ops_bf16 import linear_bf16
+    bf = torch.bfloat16
+    x = rnd(M, K, seed=1, dev=dev).to(bf).requires_grad_(True)
+    w = (rnd(N, K, seed=2, dev=dev) / math.sqrt(K)).requires_grad_(True)
+    b = rnd(N, seed=3, dev=dev).requires_grad_(True)
+    y = linear_bf16(x, w, b)
+    go = rnd(M, N, seed=4, dev=dev)
+    gx, gw, gb = torch.autograd.grad((y * go).sum(), [x, w, b])
+    xd, wd, bd = x.detach().double().requires_grad_(True), w.detach().to(bf).double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    yr = xd @ wd.t() + bd
+    close(y, yr, rtol=1e-4, atol=1e-4, what="linear bf16 fwd")
+    gob = go.to(bf).double()
+    rgx, rgw, rgb = torch.autograd.grad((yr * gob).sum(), [xd, wd, bd])
+    assert gx.dtype == bf
+    close(gx.float(), rgx, rtol=1e-2, atol=1e-2, what="dx"); close(gw, rgw, rtol=1e-4, atol=1e-3, what="dw")
+    close(gb, rgb, rtol=1e-4, atol=1e-3, what="db")
