@@ -200,16 +200,25 @@ def run_ours(args):
     rec, orig = [], LIB.call
     if rank == 0:
         def traced(name, *a):
-            if name.startswith("fn_gru_seq_"):
+            if name.startswith("fn_gru_seq_") or args.breakdown:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); rc = orig(name, *a); e1.record()
-                rec.append((e0, e1))
+                if name == "fn_tc_gemm_bf16":
+                    name = f"fn_tc_gemm_bf16 M{a[10]} N{a[11]} K{a[12]} amn{a[2]} bmn{a[5]} cbf{a[8]}"
+                rec.append((name, e0, e1))
                 return rc
             return orig(name, *a)
         LIB.call = traced
     timed(nprobe, e2e=False)                     # every rank runs it (collectives inside)
     LIB.call = orig
-    gru_ms = sum(a.elapsed_time(b) for a, b in rec) / nprobe if rec else None
+    gru_ms = sum(a.elapsed_time(b) for nm, a, b in rec if nm.startswith("fn_gru_seq_")) / nprobe if rec else None
+    breakdown = None
+    if args.breakdown and rec:
+        agg = {}
+        for nm, a, b in rec:
+            t, c = agg.get(nm, (0.0, 0))
+            agg[nm] = (t + a.elapsed_time(b), c + 1)
+        breakdown = {k: [round(v[0] / nprobe, 3), v[1] // nprobe] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
 
     if rank != 0:
         if world > 1:
@@ -248,6 +257,8 @@ def run_ours(args):
                      "step_frac_of_peak": round(flops_per_token(H) * tokens * world / (sec / args.steps) / 1e12 / (peaks["tf_sust"] * world), 5)},
         "last_step_outputs": [round(float(x), 5) for x in out],
     }
+    if breakdown:
+        line["breakdown_ms_per_step"] = breakdown       # C-ABI call -> [ms per step, calls per step] (event-timed, serial)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference(args.workload, steps=1, warmup=1)
     print(json.dumps(line))
@@ -307,6 +318,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="add per-C-ABI-call device time to the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

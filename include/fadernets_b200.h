@@ -153,6 +153,10 @@ int fn_gru_seq_fwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T
 int fn_gru_seq_bwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
                         size_t barrier_ws_bytes, void* stream);
 
+/* Profiling aid: CTA 0 of the following fn_gru_seq_*_bf16 launches writes clock64 stamps of its pipeline
+ * events into `device_buffer` ((T+1)*2*16 int64); NULL switches it off. */
+int fn_gru_debug_timeline(void* device_buffer);
+
 /* fp32 -> bf16 with arbitrary strides: dst[r*ld_dst + c] = bf16(src[r*s_r + c*s_c]) (s_r/s_c in
  * elements; s_c != 1 gives the transposed copy W_hh^T used by BPTT). */
 int fn_cast_bf16(const float* src, long long s_r, long long s_c, void* dst, long long ld_dst, long long rows,

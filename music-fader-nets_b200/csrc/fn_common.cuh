@@ -110,16 +110,16 @@ __device__ __forceinline__ void fn_red_release(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Wait until *ctr >= target.  Bounded: a lost arrival traps instead of hanging the GPU.
+// Wait until *ctr >= target.  Bounded: a lost arrival traps instead of hanging the GPU (the report is out of
+// line so the inlined wait stays a few instructions long).
+static __device__ __noinline__ void fn_spin_timeout(const unsigned* ctr, unsigned target) {
+    printf("fadernets_b200: step barrier timeout (block %d target %u have %u)\n", blockIdx.x, target, fn_ld_acquire(ctr));
+    __trap();
+}
 __device__ __forceinline__ void fn_spin_until(const unsigned* ctr, unsigned target) {
-    unsigned long long spins = 0;
+    unsigned spins = 0;
     while ((int)(fn_ld_acquire(ctr) - target) < 0) {
-        __nanosleep(20);
-        if (++spins > (1ull << 23)) {   // seconds, not microseconds: something is broken
-            printf("fadernets_b200: step barrier timeout (block %d target %u have %u)\n", blockIdx.x, target,
-                   fn_ld_acquire(ctr));
-            __trap();
-        }
+        if (++spins > (1u << 24)) fn_spin_timeout(ctr, target);
     }
 }
 

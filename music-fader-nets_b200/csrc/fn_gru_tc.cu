@@ -24,6 +24,8 @@
 // h_tau in slab tau+1; a reverse chain keeps its initial state in slab T and h_tau in slab tau -- so
 // "the state before step s" is slab tau (forward) / tau+1 (reverse) and lines up row for row with
 // gates[tau] / dg[tau] in the batched weight-gradient GEMMs.
+#include <stdlib.h>
+
 #include "fn_tc.cuh"
 
 namespace {
@@ -49,8 +51,14 @@ struct TcChain {
 struct TcLaunch {
     TcChain c[kMaxChainsTc];
     unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
-    int n_chains, nslices, B, T, H, stages;
+    long long* dbg;        // profiling aid (fn_gru_debug_timeline): [iteration][bt][16] clock64 stamps of CTA 0, or NULL
+    int n_chains, nslices, B, T, H, stages, cluster;
+    int dbg_flags;         // profiling experiments only (FN_GRU_DBGFLAGS): 1 = skip the MMAs, 2 = skip the TMA loads
 };
+#define FN_STAMP(i, bt, k)                                                                       \
+    do {                                                                                         \
+        if (P.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) P.dbg[((long long)(i) * kMaxNbt + (bt)) * 16 + (k)] = clock64(); \
+    } while (0)
 
 // ---- TMEM <-> registers, 32 lanes x W consecutive fp32 columns (thread i <-> lane base + i) --------
 template <int W>
@@ -156,12 +164,14 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f;
 }
 
-// one thread publishes a finished (step, batch tile) of this slice to the other slices of the chain
+constexpr unsigned kEpiWarps = kEpiThreads / 32;
+// Each epilogue warp publishes its part of a finished (step, batch tile) to the other slices of the chain:
+// __syncwarp orders the lanes' stores before lane 0's release (cumulativity), red.release.gpu makes them
+// visible GPU-wide before the counter moves; the proxy fence covers the consumers' TMA (async-proxy) reads.
 __device__ __forceinline__ void publish(unsigned* ctr) {
-    epi_barrier();
-    if (threadIdx.x == 64) {
-        asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy stores -> later TMA (async-proxy) reads
-        __threadfence();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         fn_red_release(ctr, 1u);
     }
 }
@@ -189,10 +199,9 @@ __device__ __forceinline__ Smem carve(uint8_t* smem_raw, int w_bytes, int stages
 // U = hidden units per CTA, NBT = 128-row batch tiles per chain.  BWD = false: N = 3U gate columns,
 // K = H.  BWD = true: N = U, K = 3H (A = gate gradients of the following step, pitch 4H).
 // =====================================================================================================
-template <int U, int NBT, bool BWD>
+template <int U, int NBT, bool BWD, int KCH>
 __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
     constexpr int N = BWD ? U : 3 * U;
-    constexpr int UT = U / 2;                                  // units per epilogue thread
     constexpr uint32_t kAccCols = NBT * N;                     // accumulators; forward: + NBT*N projection columns
     constexpr uint32_t kNeedCols = BWD ? kAccCols : 2 * kAccCols;
     constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
@@ -202,19 +211,23 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
     const int K = BWD ? 3 * H : H;
     const int nkc = K / 64;
     const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
-    const Smem sm = carve(smem_raw, nkc * w_chunk_bytes, S);
+    constexpr uint32_t stage_bytes = KCH * kATile;             // one ring stage: 128 rows x (KCH * 64) K
+    const Smem sm = carve(smem_raw, nkc * w_chunk_bytes, S * KCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
     const TcChain& c = P.c[chain];
     unsigned* gbar = P.bar + chain * 16;
     const int u0 = slice * U;
+    // cluster = `csize` consecutive slices of one chain: each streams 1/csize of every state tile and multicasts it
+    const uint32_t crank = tc::cluster_ctarank(), csize = tc::cluster_nctarank();
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1);
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&c.tmW);
         tc::prefetch_tmap(&c.tmA);
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], 8); }
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], csize); }
+        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], kEpiWarps / NBT); }
         tc::mbar_init(sm.wbar, 1);
         tc::fence_barrier_init();
     }
@@ -224,6 +237,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
     }
     tc::tc_fence_before();
     __syncthreads();
+    tc::cluster_sync();                                        // peers' barriers are initialised before any remote arrive
     tc::tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
 
@@ -232,7 +246,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
     const int n_iters = BWD ? T + 1 : T;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // Control warps run CONVERGED (all 32 lanes execute the loop, one elected lane issues the async
+        // instructions): the compiler then keeps the loop state in uniform registers and issues TMA / MMA /
+        // commit without per-instruction election loops -- these single-thread loops pace the whole kernel.
+        if (tc::elect_one()) {
             tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(nkc * w_chunk_bytes));
             for (int kc = 0; kc < nkc; ++kc) {
                 if (!BWD) {
@@ -242,235 +259,315 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
                     tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes, &c.tmW, sm.wbar, kc * 64, u0);
                 }
             }
-            uint32_t it = 0;
+        }
+        __syncwarp();
+        {
+            // ---- state-slab stream.  One thread, so everything per stage is kept to a handful of instructions:
+            // raw shared addresses, incremental stage / phase / column counters, no divisions.
+            const uint32_t rows = 128u / csize;                                   // tmA's box is 64 x rows
+            const uint32_t a0 = tc::smem_u32(sm.A) + crank * rows * 128u;
+            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
+            const int row0 = (int)(crank * rows);
+            const bool mc = csize > 1, skip_tma = (P.dbg_flags & 2) != 0;
+            const int nst = nkc / KCH;                                            // stages per (step, batch tile)
+            uint32_t st = 0, ph = 1;                                              // ph: parity that means "slot free"
             for (int i = BWD ? 1 : 0; i < n_iters; ++i) {
                 // forward: the state before step s=i;  backward (s = T-1-i): the gate gradient of step s+1
                 const int slab = BWD ? (c.reverse ? i - 1 : T - i) : (c.reverse ? T - i : i);
                 for (int bt = 0; bt < NBT; ++bt) {
+                    FN_STAMP(i, bt, 0);
                     if (i > 0) {
-                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i));
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i) * (kEpiWarps / NBT));
+                        FN_STAMP(i, bt, 1);
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
-                    for (int kc = 0; kc < nkc; ++kc, ++it) {
-                        const int st = it % S;
-                        tc::mbar_wait(&sm.empty[st], ((it / S) & 1) ^ 1);
-                        tc::mbar_arrive_expect_tx(&sm.full[st], kATile);
-                        // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
-                        const int col = (BWD && kc * 64 >= 2 * H) ? kc * 64 + H : kc * 64;
-                        tc::tma_load_3d(sm.A + (size_t)st * kATile, &c.tmA, &sm.full[st], col, bt * 128, slab);
+                    FN_STAMP(i, bt, 2);
+                    int col = 0;
+                    for (int j = 0; j < nst; ++j) {
+                        const uint32_t fb = full0 + st * 8u, sa = a0 + st * stage_bytes;
+                        tc::mbar_wait_u32(empty0 + st * 8u, ph);
+                        if (tc::elect_one()) {
+                            if (skip_tma) {
+                                tc::mbar_arrive_u32(fb);
+                            } else {
+                                tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
+#pragma unroll
+                                for (int q = 0; q < KCH; ++q) {
+                                    // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
+                                    const int cq = col + q * 64;
+                                    const int cc = (BWD && cq >= 2 * H) ? cq + H : cq;
+                                    if (mc) tc::tma_load_3d_mc_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128 + row0, slab, cmask);
+                                    else tc::tma_load_3d_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128, slab);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        col += 64 * KCH;
+                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                     }
+                    FN_STAMP(i, bt, 3);
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
             tc::mbar_wait(sm.wbar, 0);
-            uint32_t it = 0, uses = 0;
+            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
+            const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
+            const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
+            const uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4;   // descriptor address units (16 B)
+            const bool mc = csize > 1, skip_mma = (P.dbg_flags & 1) != 0;
+            const int nst = nkc / KCH;
+            uint32_t st = 0, ph = 0, uses = 0;
             for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
                 for (int bt = 0; bt < NBT; ++bt) {
                     tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
                     tc::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
-                    for (int kc = 0; kc < nkc; ++kc, ++it) {
-                        const int st = it % S;
-                        tc::mbar_wait(&sm.full[st], (it / S) & 1);
+                    uint64_t bd = bdesc0;
+                    for (int j = 0; j < nst; ++j) {
+                        tc::mbar_wait_u32(full0 + st * 8u, ph);
                         tc::tc_fence_after();
-                        const uint32_t sa = tc::smem_u32(sm.A + (size_t)st * kATile);
-                        const uint32_t sb = tc::smem_u32(sm.W + (size_t)kc * w_chunk_bytes);
+                        if (j == 0) FN_STAMP(i, bt, 4);
+                        const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
+                        if (tc::elect_one()) {
+                            if (!skip_mma) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc::umma_f16(d_tmem, tc::make_sdesc(sa + k * 32, 16, 1024), tc::make_sdesc(sb + k * 32, 16, 1024),
-                                         idesc, (kc | k) != 0);
-                        tc::umma_commit(&sm.empty[st]);
+                                for (int q = 0; q < KCH; ++q) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k),
+                                                     bd + (uint64_t)(q * b_step + 2 * k), idesc, (uint32_t)((j | q | k) != 0));
+                                }
+                            }
+                            if (mc) tc::umma_commit_mc_u32(empty0 + st * 8u, cmask);  // frees the slot in every CTA that fills it
+                            else tc::umma_commit_u32(empty0 + st * 8u);
+                            if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
+                        }
+                        __syncwarp();
+                        bd += (uint64_t)KCH * b_step;
+                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                     }
-                    tc::umma_commit(&sm.acc_full[bt]);
+                    FN_STAMP(i, bt, 5);
                 }
             }
         }
     } else {
         // ------------------------------- epilogue warps --------------------------------------------
+        // NBT == 2: warps 2..5 own batch tile 0 and warps 6..9 tile 1 (each thread: one row, all U units);
+        // NBT == 1: the two warp groups split the units of the single tile.  Per-thread work is processed in
+        // register chunks of CH units.
+        constexpr int UT = (NBT == 2) ? U : U / 2;
+        constexpr int CH = UT > 16 ? 16 : UT;
+        constexpr int NCHK = UT / CH;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read (warp id % 4)
-        const int half = (warp - 2) >> 2;        // which half of the slice's units
-        const int uu = half * UT;                // unit offset inside the slice
-        const int u = u0 + uu;
-        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const int grp = (warp - 2) >> 2;
+        const int bt = NBT == 2 ? grp : 0;
+        const int uu0 = NBT == 2 ? 0 : grp * UT; // unit offset inside the slice
+        const int b = bt * 128 + q * 32 + lane;
+        const bool row_ok = b < B;
+        const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bt * N);
+        unsigned* gflag = gbar + bt;
+        uint64_t* accf = &sm.acc_full[bt];
+        uint64_t* acce = &sm.acc_empty[bt];
+        const bool stamp = (threadIdx.x == 64);
 
         if constexpr (!BWD) {
-            float hreg[NBT][UT];
+            float hreg[UT];
             // time-invariant part of the gate pre-activations -> TMEM columns [kAccCols + bt*N, +N)
 #pragma unroll
-            for (int bt = 0; bt < NBT; ++bt) {
-                const int b = bt * 128 + q * 32 + lane;
-                const bool row_ok = b < B;
-                float pr[UT], pz[UT], pn[UT];
+            for (int ch = 0; ch < NCHK; ++ch) {
+                const int uu = uu0 + ch * CH, u = u0 + uu;
+                float pr[CH], pz[CH], pn[CH], h0v[CH];
 #pragma unroll
-                for (int j = 0; j < UT; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; hreg[bt][j] = 0.f; }
+                for (int j = 0; j < CH; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; h0v[j] = 0.f; }
                 if (row_ok) {
                     if (c.proj) {
                         const float* pj = c.proj + (long long)b * c.proj_ld + u;
-                        ldf<UT>(pj, pr); ldf<UT>(pj + H, pz); ldf<UT>(pj + 2 * H, pn);
+                        ldf<CH>(pj, pr); ldf<CH>(pj + H, pz); ldf<CH>(pj + 2 * H, pn);
                     }
-                    uint32_t hw[UT / 2];
-                    ldb_raw<UT>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
-                    unpack<UT>(hw, hreg[bt]);
+                    uint32_t hw[CH / 2];
+                    ldb_raw<CH>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
+                    unpack<CH>(hw, h0v);
                 }
 #pragma unroll
-                for (int j = 0; j < UT; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[U + uu + j]; }
-                const uint32_t tp = tmem_base + lane_sel + kAccCols + (uint32_t)(bt * N);
-                tmem_st<UT>(tp + uu, pr); tmem_st<UT>(tp + U + uu, pz); tmem_st<UT>(tp + 2 * U + uu, pn);
+                for (int j = 0; j < CH; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[U + uu + j]; hreg[ch * CH + j] = h0v[j]; }
+                const uint32_t tp = t_acc + kAccCols;
+                tmem_st<CH>(tp + uu, pr); tmem_st<CH>(tp + U + uu, pz); tmem_st<CH>(tp + 2 * U + uu, pn);
             }
             tmem_st_wait();
 
-            int id_next[NBT];
-#pragma unroll
-            for (int bt = 0; bt < NBT; ++bt) {
-                const int b = bt * 128 + q * 32 + lane;
-                id_next[bt] = (c.emb && b < B) ? c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b] : 0;
-            }
+            int id_next = (c.emb && row_ok) ? c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b] : 0;
             for (int s = 0; s < T; ++s) {
                 const int tau = c.reverse ? T - 1 - s : s;
                 const int tau_n = c.reverse ? tau - 1 : tau + 1;
+                const long long row_in = (long long)tau * B + b;           // input side is indexed by time
+                const float* e = c.emb + (long long)id_next * 3 * H + u0 + uu0;
+                const __nv_bfloat16* dp = c.dense + row_in * 3 * H + u0 + uu0;
+                // ---- operands that do not depend on the recurrence: fetch (chunk 0) before waiting for the MMA
+                float er[CH], ez[CH], en[CH];
+                uint32_t dr[CH / 2], dz[CH / 2], dn[CH / 2];
+                auto fetch = [&](int ch) {
 #pragma unroll
-                for (int bt = 0; bt < NBT; ++bt) {
-                    const int b = bt * 128 + q * 32 + lane;
-                    const bool row_ok = b < B;
-                    const long long row_in = (long long)tau * B + b;       // input side is indexed by time
-                    // ---- operands that do not depend on the recurrence: fetch before waiting for the MMA
-                    float er[UT], ez[UT], en[UT];
-                    uint32_t dr[UT / 2], dz[UT / 2], dn[UT / 2];
-#pragma unroll
-                    for (int j = 0; j < UT; ++j) { er[j] = 0.f; ez[j] = 0.f; en[j] = 0.f; }
-                    if (row_ok && c.emb) {
-                        const float* e = c.emb + (long long)id_next[bt] * 3 * H + u;
-                        ldf<UT>(e, er); ldf<UT>(e + H, ez); ldf<UT>(e + 2 * H, en);
-                        if (s + 1 < T) id_next[bt] = c.ids[(long long)tau_n * B + b];
-                    }
+                    for (int j = 0; j < CH; ++j) { er[j] = 0.f; ez[j] = 0.f; en[j] = 0.f; }
+                    if (row_ok && c.emb) { ldf<CH>(e + ch * CH, er); ldf<CH>(e + H + ch * CH, ez); ldf<CH>(e + 2 * H + ch * CH, en); }
                     if (row_ok && c.dense) {
-                        const __nv_bfloat16* dp = c.dense + row_in * 3 * H + u;
-                        ldb_raw<UT>(dp, dr, false); ldb_raw<UT>(dp + H, dz, false); ldb_raw<UT>(dp + 2 * H, dn, false);
+                        ldb_raw<CH>(dp + ch * CH, dr, false); ldb_raw<CH>(dp + H + ch * CH, dz, false);
+                        ldb_raw<CH>(dp + 2 * H + ch * CH, dn, false);
                     }
-                    tc::mbar_wait(&sm.acc_full[bt], s & 1);
-                    tc::tc_fence_after();
-                    const uint32_t ta = tmem_base + lane_sel + (uint32_t)(bt * N) + uu;
-                    const uint32_t tp = ta + kAccCols;
-                    float a[UT], p[UT], r[UT], z[UT], n[UT], g[UT];
-                    tmem_ld<UT>(ta, a); tmem_ld<UT>(tp, p);
-                    if (c.dense) { float t[UT]; unpack<UT>(dr, t);
+                };
+                fetch(0);
+                if (row_ok && c.emb && s + 1 < T) id_next = c.ids[(long long)tau_n * B + b];
+                if (stamp) FN_STAMP(s, bt, 6);
+                tc::mbar_wait_warp(accf, s & 1);
+                tc::tc_fence_after();
+                if (stamp) FN_STAMP(s, bt, 7);
+                float r[CH], z[CH], n[CH], g[CH];
 #pragma unroll
-                        for (int j = 0; j < UT; ++j) er[j] += t[j]; }
+                for (int ch = 0; ch < NCHK; ++ch) {
+                    const int uu = uu0 + ch * CH, u = u0 + uu;
+                    if (ch > 0) fetch(ch);
+                    const uint32_t ta = t_acc + uu, tp = ta + kAccCols;
+                    float a[CH], p[CH];
+                    tmem_ld<CH>(ta, a); tmem_ld<CH>(tp, p);
+                    if (c.dense) { float t[CH]; unpack<CH>(dr, t);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) r[j] = fast_sigmoid(a[j] + p[j] + er[j]);
-                    tmem_ld<UT>(ta + U, a); tmem_ld<UT>(tp + U, p);
-                    if (c.dense) { float t[UT]; unpack<UT>(dz, t);
+                        for (int j = 0; j < CH; ++j) er[j] += t[j]; }
 #pragma unroll
-                        for (int j = 0; j < UT; ++j) ez[j] += t[j]; }
+                    for (int j = 0; j < CH; ++j) r[j] = fast_sigmoid(a[j] + p[j] + er[j]);
+                    tmem_ld<CH>(ta + U, a); tmem_ld<CH>(tp + U, p);
+                    if (c.dense) { float t[CH]; unpack<CH>(dz, t);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) z[j] = fast_sigmoid(a[j] + p[j] + ez[j]);
-                    tmem_ld<UT>(ta + 2 * U, a); tmem_ld<UT>(tp + 2 * U, p);
-                    // accumulator consumed: the tensor core may start the next step of this tile
-                    tc::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&sm.acc_empty[bt]);
-                    if (c.dense) { float t[UT]; unpack<UT>(dn, t);
+                        for (int j = 0; j < CH; ++j) ez[j] += t[j]; }
 #pragma unroll
-                        for (int j = 0; j < UT; ++j) en[j] += t[j]; }
+                    for (int j = 0; j < CH; ++j) z[j] = fast_sigmoid(a[j] + p[j] + ez[j]);
+                    tmem_ld<CH>(ta + 2 * U, a); tmem_ld<CH>(tp + 2 * U, p);
+                    if (ch == NCHK - 1) {
+                        // accumulator consumed: the tensor core may start the next step of this tile
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(acce);
+                    }
+                    if (c.dense) { float t[CH]; unpack<CH>(dn, t);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) {
+                        for (int j = 0; j < CH; ++j) en[j] += t[j]; }
+                    float hn[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
                         g[j] = a[j] + sm.bias[2 * U + uu + j];
                         n[j] = fast_tanh(p[j] + en[j] + r[j] * g[j]);
-                        hreg[bt][j] = (1.f - z[j]) * n[j] + z[j] * hreg[bt][j];
+                        hn[j] = (1.f - z[j]) * n[j] + z[j] * hreg[ch * CH + j];
+                        hreg[ch * CH + j] = hn[j];
                     }
                     if (row_ok) {
-                        stb<UT>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hreg[bt]);
-                        if (c.gates) {
+                        stb<CH>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hn);
+                        if (NCHK > 1 && c.gates) {       // several chunks: save the gates right away
                             __nv_bfloat16* gsv = c.gates + row_in * 4 * H + u;
-                            stb<UT>(gsv, r); stb<UT>(gsv + H, z); stb<UT>(gsv + 2 * H, n); stb<UT>(gsv + 3 * H, g);
-                        }
-                        if (s == T - 1 && c.h_final) {          // caller-chosen offset / pitch: no alignment assumed
-                            float* hf = c.h_final + (long long)b * c.h_final_ld + u;
-#pragma unroll
-                            for (int j = 0; j < UT; ++j) hf[j] = hreg[bt][j];
+                            stb<CH>(gsv, r); stb<CH>(gsv + H, z); stb<CH>(gsv + 2 * H, n); stb<CH>(gsv + 3 * H, g);
                         }
                     }
-                    if (s + 1 < T) publish(gbar + bt);
+                }
+                if (stamp) FN_STAMP(s, bt, 9);
+                if (s + 1 < T) publish(gflag);                  // the next step only needs the state
+                if (stamp) FN_STAMP(s, bt, 10);
+                if (row_ok) {
+                    if (NCHK == 1 && c.gates) {                 // off the critical path: after the publish
+                        __nv_bfloat16* gsv = c.gates + row_in * 4 * H + u0 + uu0;
+                        stb<CH>(gsv, r); stb<CH>(gsv + H, z); stb<CH>(gsv + 2 * H, n); stb<CH>(gsv + 3 * H, g);
+                    }
+                    if (s == T - 1 && c.h_final) {              // caller-chosen offset / pitch: no alignment assumed
+                        float* hf = c.h_final + (long long)b * c.h_final_ld + u0 + uu0;
+#pragma unroll
+                        for (int j = 0; j < UT; ++j) hf[j] = hreg[j];
+                    }
                 }
             }
         } else {
-            float carry[NBT][UT];
+            float carry[UT];
 #pragma unroll
-            for (int bt = 0; bt < NBT; ++bt)
-#pragma unroll
-                for (int j = 0; j < UT; ++j) carry[bt][j] = 0.f;
+            for (int j = 0; j < UT; ++j) carry[j] = 0.f;
             for (int i = 0; i <= T; ++i) {
                 const int s = T - 1 - i;
                 const int tau = c.reverse ? T - 1 - s : s;
+                const long long row = (long long)tau * B + b;
+                // ---- saved forward values and incoming gradients: fetch (chunk 0) before waiting for the MMA
+                uint32_t wr[CH / 2], wz[CH / 2], wn[CH / 2], wg[CH / 2], wh[CH / 2];
+                float din[CH];
+                auto fetch = [&](int ch) {
+                    const int u = u0 + uu0 + ch * CH;
 #pragma unroll
-                for (int bt = 0; bt < NBT; ++bt) {
-                    const int b = bt * 128 + q * 32 + lane;
-                    const bool row_ok = b < B;
-                    const long long row = (long long)tau * B + b;
-                    // ---- saved forward values and incoming gradients: fetch before waiting for the MMA
-                    uint32_t wr[UT / 2], wz[UT / 2], wn[UT / 2], wg[UT / 2], wh[UT / 2];
-                    float din[UT];
+                    for (int j = 0; j < CH / 2; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
 #pragma unroll
-                    for (int j = 0; j < UT / 2; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
-#pragma unroll
-                    for (int j = 0; j < UT; ++j) din[j] = 0.f;
+                    for (int j = 0; j < CH; ++j) din[j] = 0.f;
                     if (row_ok && s >= 0) {
                         const __nv_bfloat16* gsv = c.gates + row * 4 * H + u;
-                        ldb_raw<UT>(gsv, wr, false); ldb_raw<UT>(gsv + H, wz, false);
-                        ldb_raw<UT>(gsv + 2 * H, wn, false); ldb_raw<UT>(gsv + 3 * H, wg, false);
-                        ldb_raw<UT>(c.hsx + (row + (c.reverse ? B : 0)) * H + u, wh, false);   // the state before step s
+                        ldb_raw<CH>(gsv, wr, false); ldb_raw<CH>(gsv + H, wz, false);
+                        ldb_raw<CH>(gsv + 2 * H, wn, false); ldb_raw<CH>(gsv + 3 * H, wg, false);
+                        ldb_raw<CH>(c.hsx + (row + (c.reverse ? B : 0)) * H + u, wh, false);   // the state before step s
                         if (c.dhs) {
-                            if (c.dhs_f32) ldf<UT>(reinterpret_cast<const float*>(c.dhs) + row * H + u, din);
+                            if (c.dhs_f32) ldf<CH>(reinterpret_cast<const float*>(c.dhs) + row * H + u, din);
                             else {
-                                uint32_t wd[UT / 2];
-                                ldb_raw<UT>(reinterpret_cast<const __nv_bfloat16*>(c.dhs) + row * H + u, wd, false);
-                                unpack<UT>(wd, din);
+                                uint32_t wd[CH / 2];
+                                ldb_raw<CH>(reinterpret_cast<const __nv_bfloat16*>(c.dhs) + row * H + u, wd, false);
+                                unpack<CH>(wd, din);
                             }
                         }
                         if (s == T - 1 && c.dh_final) {
                             const float* df = c.dh_final + (long long)b * c.dh_final_ld + u;
 #pragma unroll
-                            for (int j = 0; j < UT; ++j) din[j] += __ldg(df + j);
+                            for (int j = 0; j < CH; ++j) din[j] += __ldg(df + j);
                         }
                     }
-                    float dh[UT];
+                };
+                fetch(0);
+                if (i > 0) {
+                    tc::mbar_wait_warp(accf, (i - 1) & 1);
+                    tc::tc_fence_after();
+                }
+                float o_i[CH];
+#pragma unroll
+                for (int ch = 0; ch < NCHK; ++ch) {
+                    const int uu = uu0 + ch * CH, u = u0 + uu;
+                    if (ch > 0) fetch(ch);
+                    float dh[CH];
                     if (i > 0) {
-                        tc::mbar_wait(&sm.acc_full[bt], (i - 1) & 1);
-                        tc::tc_fence_after();
-                        tmem_ld<UT>(tmem_base + lane_sel + (uint32_t)(bt * N) + uu, dh);
-                        tc::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&sm.acc_empty[bt]);
+                        tmem_ld<CH>(t_acc + uu, dh);
+                        if (ch == NCHK - 1) {
+                            tc::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(acce);
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < UT; ++j) dh[j] = 0.f;
+                        for (int j = 0; j < CH; ++j) dh[j] = 0.f;
                     }
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) dh[j] += carry[bt][j] + din[j];
+                    for (int j = 0; j < CH; ++j) dh[j] += carry[ch * CH + j] + din[j];
                     if (s < 0) {
-                        if (row_ok) stf<UT>(c.dh0 + (long long)b * H + u, dh);
+                        if (row_ok) stf<CH>(c.dh0 + (long long)b * H + u, dh);
                         continue;
                     }
-                    float r[UT], z[UT], n[UT], g[UT], hp[UT], o_r[UT], o_z[UT], o_n[UT], o_i[UT];
-                    unpack<UT>(wr, r); unpack<UT>(wz, z); unpack<UT>(wn, n); unpack<UT>(wg, g); unpack<UT>(wh, hp);
+                    float r[CH], z[CH], n[CH], g[CH], hp[CH], o_r[CH], o_z[CH], o_n[CH];
+                    unpack<CH>(wr, r); unpack<CH>(wz, z); unpack<CH>(wn, n); unpack<CH>(wg, g); unpack<CH>(wh, hp);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) {
+                    for (int j = 0; j < CH; ++j) {
                         const float dnp = dh[j] * (1.f - z[j]) * (1.f - n[j] * n[j]);
                         o_z[j] = dh[j] * (hp[j] - n[j]) * z[j] * (1.f - z[j]);
                         o_r[j] = dnp * g[j] * r[j] * (1.f - r[j]);
                         o_n[j] = dnp * r[j];
                         o_i[j] = dnp;
-                        carry[bt][j] = dh[j] * z[j];
+                        carry[ch * CH + j] = dh[j] * z[j];
                     }
                     if (row_ok) {
                         __nv_bfloat16* dgp = c.dg + row * 4 * H + u;
-                        stb<UT>(dgp, o_r); stb<UT>(dgp + H, o_z); stb<UT>(dgp + 2 * H, o_i); stb<UT>(dgp + 3 * H, o_n);
+                        stb<CH>(dgp, o_r); stb<CH>(dgp + H, o_z); stb<CH>(dgp + 3 * H, o_n);
+                        if (NCHK > 1) stb<CH>(dgp + 2 * H, o_i);
                     }
-                    publish(gbar + bt);
                 }
+                if (s < 0) continue;
+                publish(gflag);                              // the recurrence consumes (dr, dz, dn*r) only
+                if (NCHK == 1 && row_ok) stb<CH>(c.dg + row * 4 * H + u0 + uu0 + 2 * H, o_i);
             }
         }
         tc::tc_fence_before();
@@ -480,12 +577,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, kTmemCols);
     }
+    tc::cluster_sync();                                        // no CTA leaves while peers may still signal its barriers
 }
 
 // ---- host -------------------------------------------------------------------------------------------
+long long* g_dbg = nullptr;
 constexpr size_t kSmemTail = 1024 /*align*/ + 512 /*barriers*/ + 3 * 64 * 4 /*bias*/;
 
 size_t tc_w_bytes(int U, int H, bool bwd) { return (size_t)((bwd ? 3 * H : H) / 64) * (bwd ? U : 3 * U) * 128; }
+// K chunks (of 64) per ring stage: 2 whenever the chunk count is even (amortises the per-stage barrier work)
+int tc_kch(int H, bool bwd) { return (((bwd ? 3 * H : H) / 64) % 2 == 0) ? 2 : 1; }
+// ring depth in 16 KB tiles
 int tc_stages(int U, int H, bool bwd) {
     const long long room = (long long)fn_max_smem_optin() - (long long)tc_w_bytes(U, H, bwd) - (long long)kSmemTail;
     long long s = room / kATile;
@@ -513,9 +615,14 @@ int fn_make_tmap_bf16_3d(CUtensorMap* out, const void* base, unsigned long long 
 // that still leaves >= 2 ring stages and fits the grid on the machine.
 int pick_u_tc(int n_chains, int H, bool bwd) {
     const int sms = fn_num_sms();
+    // the state slab is streamed through a ring whose depth (not L2 bandwidth) bounds the step: Little's law,
+    // bytes in flight / TMA round trip.  Prefer the slice width that leaves >= 6 stages.
+    static const int force_u = getenv("FN_GRU_U") ? atoi(getenv("FN_GRU_U")) : 0;
+    for (int pass = 0; pass < 2; ++pass)
     for (int U : {32, 16}) {
+        if (force_u && U != force_u) continue;
         if (H % U) continue;
-        if (tc_stages(U, H, false) < 2 || tc_stages(U, H, true) < 2) continue;
+        if (tc_stages(U, H, false) < (pass == 0 ? 6 : 2) || tc_stages(U, H, true) < (pass == 0 ? 6 : 2)) continue;
         if ((long long)n_chains * (H / U) > sms) continue;
         return U;
     }
@@ -523,19 +630,48 @@ int pick_u_tc(int n_chains, int H, bool bwd) {
     return 0;
 }
 
-template <int U, int NBT, bool BWD>
+template <int U, int NBT, bool BWD, int KCH>
 int launch_tc(const TcLaunch& P, cudaStream_t st) {
-    const size_t smem = tc_w_bytes(U, P.H, BWD) + (size_t)P.stages * kATile + kSmemTail;
-    const void* fn = (const void*)gru_tc_kernel<U, NBT, BWD>;
+    const size_t smem = tc_w_bytes(U, P.H, BWD) + (size_t)P.stages * KCH * kATile + kSmemTail;
+    const void* fn = (const void*)gru_tc_kernel<U, NBT, BWD, KCH>;
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(P.n_chains * P.nslices);
+    cfg.blockDim = dim3(kThreadsTc);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = P.cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;           // every CTA must be co-resident: they wait on each other
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    // all CTAs must be resident at once (slices of a chain wait for each other every step)
+    int max_clusters = 0;
+    FN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
+    FN_REQUIRE(max_clusters * P.cluster >= P.n_chains * P.nslices,
+               "fn_gru_seq_bf16: %d CTAs in clusters of %d are not co-resident (max %d clusters)", P.n_chains * P.nslices,
+               P.cluster, max_clusters);
     void* args[] = {(void*)&P};
-    FN_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(P.n_chains * P.nslices), dim3(kThreadsTc), args, smem, st));
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess) {                                  // cooperative + cluster refused: residency was checked above
+        (void)cudaGetLastError();
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelExC(&cfg, fn, args);
+    }
+    FN_CHECK_CUDA(e);
     return FN_OK;
 }
+template <bool BWD, int KCH>
+int dispatch_tc2(int U, int nbt, const TcLaunch& P, cudaStream_t st) {
+    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD, KCH>(P, st) : launch_tc<32, 2, BWD, KCH>(P, st);
+    return nbt == 1 ? launch_tc<16, 1, BWD, KCH>(P, st) : launch_tc<16, 2, BWD, KCH>(P, st);
+}
 template <bool BWD>
-int dispatch_tc(int U, int nbt, const TcLaunch& P, cudaStream_t st) {
-    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD>(P, st) : launch_tc<32, 2, BWD>(P, st);
-    return nbt == 1 ? launch_tc<16, 1, BWD>(P, st) : launch_tc<16, 2, BWD>(P, st);
+int dispatch_tc(int U, int nbt, int kch, const TcLaunch& P, cudaStream_t st) {
+    return kch == 2 ? dispatch_tc2<BWD, 2>(U, nbt, P, st) : dispatch_tc2<BWD, 1>(U, nbt, P, st);
 }
 
 int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
@@ -547,6 +683,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
     FN_REQUIRE(barrier_ws && ws_bytes >= (size_t)64 * n_chains, "fn_gru_seq_bf16: barrier_ws too small");
     FN_CHECK_CUDA(cudaMemsetAsync(barrier_ws, 0, (size_t)64 * n_chains, st));
     const int nbt = (B + 127) / 128;
+    static const int force_cs = getenv("FN_GRU_CLUSTER") ? atoi(getenv("FN_GRU_CLUSTER")) : 0;
     int done = 0;
     while (done < n_chains) {
         int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc, U = 0;
@@ -555,6 +692,10 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         FN_REQUIRE(group >= 1, "fn_gru_seq_bf16: H=%d not supported by the tcgen05 path", H);
         TcLaunch P;
         memset(&P, 0, sizeof(P));
+        // cluster of consecutive slices that share (multicast) the streamed state tiles
+        int cs = force_cs ? force_cs : 4;
+        while (cs > 1 && ((H / U) % cs != 0 || 128 % cs != 0)) cs >>= 1;
+        P.cluster = cs;
         for (int i = 0; i < group; ++i) {
             const FnGruChainBf16& s = chains[done + i];
             TcChain& d = P.c[i];
@@ -565,13 +706,13 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
                 FN_REQUIRE(!s.emb || s.ids, "fn_gru_seq_fwd_bf16: chain %d has emb without ids", done + i);
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh, 3ull * H, H, H, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, H, H, 128, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, H, H, 128 / cs, 64);
                 if (rc) return rc;
             } else {
                 FN_REQUIRE(s.w_hh_t && s.gates && s.dg && s.dh0, "fn_gru_seq_bwd_bf16: chain %d misses buffers", done + i);
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh_t, H, 3ull * H, 3ull * H, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, 4ull * H, 4ull * H, 128, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, 4ull * H, 4ull * H, 128 / cs, 64);
                 if (rc) return rc;
             }
             d.b_hh = s.b_hh; d.emb = s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
@@ -584,8 +725,12 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
         P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H;
-        P.stages = tc_stages(U, H, bwd);
-        const int rc = bwd ? dispatch_tc<true>(U, nbt, P, st) : dispatch_tc<false>(U, nbt, P, st);
+        const int kch = tc_stages(U, H, bwd) >= 4 ? tc_kch(H, bwd) : 1;
+        P.stages = tc_stages(U, H, bwd) / kch;               // in units of (kch * 16 KB) stages
+        P.dbg = g_dbg;
+        static const int dbg_flags = getenv("FN_GRU_DBGFLAGS") ? atoi(getenv("FN_GRU_DBGFLAGS")) : 0;
+        P.dbg_flags = dbg_flags;
+        const int rc = bwd ? dispatch_tc<true>(U, nbt, kch, P, st) : dispatch_tc<false>(U, nbt, kch, P, st);
         if (rc != FN_OK) return rc;
         done += group;
     }
@@ -593,6 +738,13 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
 }
 
 }  // namespace
+
+// Profiling aid: when set (device buffer of >= (T+1)*2*16 int64), CTA 0 of every following launch records
+// clock64 stamps of its pipeline events (see FN_STAMP).  NULL switches it off.  Not part of the product path.
+extern "C" int fn_gru_debug_timeline(void* device_buffer) {
+    g_dbg = reinterpret_cast<long long*>(device_buffer);
+    return FN_OK;
+}
 
 extern "C" int fn_gru_seq_fwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
                                    size_t barrier_ws_bytes, void* stream) {

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "fn_gru_seq_ctas_per_chain": (I, [I]),
     "fn_gru_seq_fwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_bwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
+    "fn_gru_debug_timeline": (I, [V]),
     "fn_cast_bf16": (I, [V, LL, LL, V, LL, LL, LL, V]),
     "fn_ids_to_onehot_bf16": (I, [V, LL, I, LL, V, V]),
     "fn_time_sum_bf16": (I, [V, I, I, I, V, V, V]),

@@ -64,6 +64,8 @@ def test_bf16_train_step_vs_oracle(dev, variant, H, Z, K, B, T):
     bad = []
     params = dict(model.named_parameters())
     for k, ref in grads.items():
+        if k in ("linear_out_r.bias", "linear_out_n.bias"):
+            continue      # mathematically zero (time-axis log-softmax is shift invariant): rounding noise only
         got = params[k].grad.cpu()
         assert torch.isfinite(got).all(), k
         scale = max(float(ref.abs().max()), 1e-6)

@@ -1,0 +1,192 @@
+// Micro-benchmark (profiling aid, not part of the product): issue cost / throughput of tcgen05.mma as a function
+// of N, from ONE issuing thread of one CTA per SM, operands in (garbage) shared memory, accumulator in TMEM.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I music-fader-nets_b200/csrc -o /tmp/ubench_tc tools/ubench_tc.cu
+#include <cstdio>
+#include <cstdlib>
+#include "fn_tc.cuh"
+void fn_set_error(const char*, ...) {}
+int fn_num_sms() { return 148; }
+int fn_max_smem_optin() { return 232448; }
+
+template <int CONVERGED>
+__global__ void __launch_bounds__(128, 1) k_mma(int N, int n_mma, int reps, long long* out, int a_from_tmem) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (warp == 1) tc::tmem_alloc(&tslot, 512);
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t tmem = tslot;
+    if (warp == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+        const uint64_t ad = tc::make_sdesc(tc::smem_u32(smem), 16, 1024), bd = tc::make_sdesc(tc::smem_u32(smem) + 65536, 16, 1024);
+        long long best = 1ll << 60, best_issue = 1ll << 60;
+        for (int r = 0; r < reps; ++r) {
+            __syncwarp();
+            const long long t0 = clock64();
+            if (CONVERGED) {
+                for (int i = 0; i < n_mma; ++i) {
+                    uint32_t pred;
+                    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+                    if (pred) tc::umma_f16(tmem, ad + (uint64_t)(2 * (i & 3) + 1024 * ((i >> 2) & 3)), bd + (uint64_t)(2 * (i & 3)), idesc, i != 0);
+                    __syncwarp();
+                }
+            } else if (lane == 0) {
+                for (int i = 0; i < n_mma; ++i)
+                    tc::umma_f16(tmem, ad + (uint64_t)(2 * (i & 3) + 1024 * ((i >> 2) & 3)), bd + (uint64_t)(2 * (i & 3)), idesc, i != 0);
+            }
+            const long long t1 = clock64();
+            if (lane == 0) { tc::umma_commit(&bar); }
+            tc::mbar_wait(&bar, r & 1);
+            const long long t2 = clock64();
+            if (t2 - t0 < best) best = t2 - t0;
+            if (t1 - t0 < best_issue) best_issue = t1 - t0;
+        }
+        if (lane == 0 && blockIdx.x == 0) { out[0] = best; out[1] = best_issue; }
+    }
+    tc::tc_fence_before(); __syncthreads();
+    if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 512); }
+}
+
+// cost of mbarrier ops / TMA-less handshakes from one thread
+__global__ void k_bar(int n, long long* out) {
+    __shared__ uint64_t bar[2];
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::fence_barrier_init();
+        long long t0 = clock64();
+        uint32_t ph = 0;
+        for (int i = 0; i < n; ++i) { tc::mbar_arrive(&bar[0]); tc::mbar_wait(&bar[0], ph); ph ^= 1; }
+        long long t1 = clock64();
+        out[0] = t1 - t0;
+        t0 = clock64();
+        for (int i = 0; i < n; ++i) { tc::mbar_arrive_expect_tx(&bar[1], 0); }
+        t1 = clock64();
+        out[1] = t1 - t0;
+    }
+}
+
+// producer <-> MMA-thread ring handshake, optional MMAs, optional bystander warps waiting on another barrier
+__global__ void __launch_bounds__(320, 1) k_ring(int n, int stages, int mmas, int N, int bystanders, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[8], empty[8], other, done;
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(&other, 1); tc::mbar_init(&done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(&tslot, 512);
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t tmem = tslot;
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t st = 0, ph = 1;
+            const uint32_t f0 = tc::smem_u32(full), e0 = tc::smem_u32(empty);
+            const long long t0 = clock64();
+            for (int i = 0; i < n; ++i) {
+                tc::mbar_wait_u32(e0 + st * 8, ph);
+                tc::mbar_arrive_u32(f0 + st * 8);
+                if (++st == (uint32_t)stages) { st = 0; ph ^= 1; }
+            }
+            out[2] = clock64() - t0;
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+            const uint64_t ad = tc::make_sdesc(tc::smem_u32(smem), 16, 1024), bd = tc::make_sdesc(tc::smem_u32(smem) + 65536, 16, 1024);
+            uint32_t st = 0, ph = 0;
+            const uint32_t f0 = tc::smem_u32(full), e0 = tc::smem_u32(empty);
+            const long long t0 = clock64();
+            for (int i = 0; i < n; ++i) {
+                tc::mbar_wait_u32(f0 + st * 8, ph);
+                tc::tc_fence_after();
+                for (int k = 0; k < mmas; ++k) tc::umma_f16(tmem, ad + (uint64_t)(2 * (k & 3)), bd + (uint64_t)(2 * (k & 3)), idesc, 1);
+                tc::umma_commit_u32(e0 + st * 8);
+                if (++st == (uint32_t)stages) { st = 0; ph ^= 1; }
+            }
+            tc::umma_commit(&done);
+            tc::mbar_wait(&done, 0);
+            out[0] = clock64() - t0;
+            tc::mbar_arrive(&other);
+        }
+    } else {
+        if (bystanders == 1) tc::mbar_wait_warp(&other, 0);
+        else if (bystanders == 2) tc::mbar_wait(&other, 0);
+    }
+    tc::tc_fence_before(); __syncthreads();
+    if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 512); }
+}
+
+// MMA stream from one thread with a tcgen05.commit (to a barrier nobody waits on) every `every` groups of `mmas`
+__global__ void __launch_bounds__(128, 1) k_commit(int n, int mmas, int every, int N, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t dummy, done;
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { tc::mbar_init(&dummy, 1 << 20); tc::mbar_init(&done, 1); tc::fence_barrier_init(); }
+    if (warp == 1) tc::tmem_alloc(&tslot, 512);
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t tmem = tslot;
+    if (warp == 0 && lane == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+        const uint64_t ad = tc::make_sdesc(tc::smem_u32(smem), 16, 1024), bd = tc::make_sdesc(tc::smem_u32(smem) + 65536, 16, 1024);
+        const uint32_t d0 = tc::smem_u32(&dummy);
+        const long long t0 = clock64();
+        for (int i = 0; i < n; ++i) {
+            for (int k = 0; k < mmas; ++k) tc::umma_f16(tmem, ad + (uint64_t)(2 * (k & 3)), bd + (uint64_t)(2 * (k & 3)), idesc, 1);
+            if (every && (i % every) == every - 1) tc::umma_commit_u32(d0);
+        }
+        tc::umma_commit(&done);
+        tc::mbar_wait(&done, 0);
+        out[0] = clock64() - t0;
+    }
+    tc::tc_fence_before(); __syncthreads();
+    if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 512); }
+}
+
+int main() {
+    {
+        long long* o; cudaMallocManaged(&o, 64);
+        cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int N : {48, 96})
+            for (int ev : {0, 1, 2, 4})
+                for (int mm : {4, 8}) {
+                    k_commit<<<1, 128, 200 * 1024>>>(1000, mm, ev, N, o); cudaDeviceSynchronize();
+                    printf("commit: N=%d mmas/group=%d commit every %d groups: %.1f cyc/group = %.1f cyc/MMA  %s\n", N, mm, ev, o[0] / 1000.0,
+                           o[0] / 1000.0 / mm, cudaGetErrorString(cudaGetLastError()));
+                }
+    }
+    {
+        long long* o; cudaMallocManaged(&o, 64);
+        cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int by : {0, 1, 2})
+            for (int mm : {0, 8})
+                for (int stg : {1, 4}) {
+                    k_ring<<<1, 320, 200 * 1024>>>(2000, stg, mm, 48, by, o); cudaDeviceSynchronize();
+                    printf("ring: bystanders=%d (0 none,1 lane0-poll,2 all-lane poll) mmas/stage=%d stages=%d: %.1f cyc/iter (producer loop %.1f)  %s\n", by, mm, stg,
+                           o[0] / 2000.0, o[2] / 2000.0, cudaGetErrorString(cudaGetLastError()));
+                }
+    }
+    long long* out; cudaMallocManaged(&out, 64);
+    const int smem = 200 * 1024;
+    cudaFuncSetAttribute(k_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int n_mma = 256;
+    for (int grid : {1, 148}) {
+        for (int N : {16, 32, 48, 96, 128, 192, 256}) {
+            k_mma<0><<<grid, 128, smem>>>(N, n_mma, 5, out, 0); cudaDeviceSynchronize();
+            long long a = out[0], ai = out[1];
+            k_mma<1><<<grid, 128, smem>>>(N, n_mma, 5, out, 0); cudaDeviceSynchronize();
+            printf("grid %3d  M=128 N=%3d K=16: lane0-only %.1f cyc/MMA (issue %.1f) | elect-converged %.1f cyc/MMA (issue %.1f) | ideal %.1f  err=%s\n",
+                   grid, N, (double)a / n_mma, (double)ai / n_mma, (double)out[0] / n_mma, (double)out[1] / n_mma, 128.0 * N / 256, cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    k_bar<<<1, 32>>>(1000, out); cudaDeviceSynchronize();
+    printf("mbarrier arrive+try_wait round trip: %.1f cyc; arrive.expect_tx: %.1f cyc\n", out[0] / 1000.0, out[1] / 1000.0);
+    return 0;
+}
