@@ -63,6 +63,14 @@ int fn_tc_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B,
                     void* C, long long ldc, int c_bf16, const float* bias, int M, int N, int K, int accumulate,
                     void* stream);
 
+/* Split-K variant for products with few output tiles and a very long K (the T*B-row weight gradients):
+ * `splits` CTAs per output tile each reduce a K range into `workspace` (fn_tc_gemm_splitk_ws_bytes), then a
+ * fixed-order reduction applies bias / accumulate -- deterministic, no float atomics. */
+size_t fn_tc_gemm_splitk_ws_bytes(int M, int N, int splits);
+int fn_tc_gemm_bf16_splitk(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                           void* C, long long ldc, int c_bf16, const float* bias, int M, int N, int K, int accumulate,
+                           int splits, void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Persistent time-loop GRU ("gate block": recurrent GEMM + sigma/tanh/Hadamard per step).
  * One launch runs `n_chains` independent recurrences; each chain is split over hidden-unit
@@ -130,11 +138,11 @@ typedef struct FnGruChainBf16 {
     const void* w_hh;         /* bf16 [3H][H]            (forward)                            */
     const void* w_hh_t;       /* bf16 [H][3H] = W_hh^T   (backward)                           */
     const float* b_hh;        /* fp32 [3H]                                                    */
-    const float* emb;         /* fp32 [Vin][3H] = W_ih[:, :Vin]^T, or NULL                    */
+    const void* emb;          /* bf16 [Vin][3H] = W_ih[:, :Vin]^T, or NULL (input = token gather) */
     const int32_t* ids;       /* [T][B] token ids by time, or NULL                            */
     const float* proj;        /* fp32 [B][3H] (row stride proj_ld; 0 = one broadcast row) / NULL */
     long long proj_ld;
-    const void* dense;        /* bf16 [T][B][3H] by time, or NULL                             */
+    const void* dense;        /* bf16 [T][B][3H] by time, or NULL (input = dense stream; excludes emb) */
     int32_t reverse;
     int32_t dhs_f32;          /* dtype of dhs: 0 = bf16, 1 = fp32                             */
     void* hsx;                /* bf16 [T+1][B][H] (see above)                                 */

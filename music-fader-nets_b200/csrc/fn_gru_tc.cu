@@ -31,7 +31,9 @@
 namespace {
 
 constexpr int kMaxChainsTc = 4;
-constexpr int kThreadsTc = 320;           // 2 control warps + 8 epilogue warps
+constexpr int kThreadsTc = 352;           // 2 control warps + 8 epilogue warps + 1 weight-tail producer warp
+constexpr int kWTailWarp = 10;
+constexpr int kMaxWst = 8;                // slots of the streamed-weight ring
 constexpr int kEpiThreads = 256;
 constexpr int kATile = 128 * 64 * 2;      // 16 KB: 128 batch rows x 64 K (bf16), one 128B-swizzle atom wide
 constexpr int kMaxStages = 8;
@@ -40,7 +42,7 @@ constexpr int kMaxNbt = 2;
 struct TcChain {
     CUtensorMap tmW;       // resident operand: fwd W_hh [3H][H]; bwd W_hh^T [H][3H]   (box 64 x U)
     CUtensorMap tmA;       // streamed operand, 3-D [slabs][B][K]                      (box 64 x 128 x 1)
-    const float* b_hh; const float* emb; const int32_t* ids; const float* proj; long long proj_ld;
+    const float* b_hh; const __nv_bfloat16* emb; const int32_t* ids; const float* proj; long long proj_ld;
     const __nv_bfloat16* dense;
     __nv_bfloat16* hsx; __nv_bfloat16* gates; float* h_final; long long h_final_ld;
     const void* dhs; const float* dh_final; long long dh_final_ld;
@@ -53,6 +55,7 @@ struct TcLaunch {
     unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
     long long* dbg;        // profiling aid (fn_gru_debug_timeline): [iteration][bt][16] clock64 stamps of CTA 0, or NULL
     int n_chains, nslices, B, T, H, stages, cluster;
+    int kres, wst;         // resident K chunks of the weight slice; ring slots for the streamed rest (0 = all resident)
     int dbg_flags;         // profiling experiments only (FN_GRU_DBGFLAGS): 1 = skip the MMAs, 2 = skip the TMA loads
 };
 #define FN_STAMP(i, bt, k)                                                                       \
@@ -177,20 +180,22 @@ __device__ __forceinline__ void publish(unsigned* ctr) {
 }
 
 struct Smem {
-    uint8_t* W; uint8_t* A;
-    uint64_t *full, *empty, *acc_full, *acc_empty, *wbar;
+    uint8_t* W; uint8_t* WR; uint8_t* A;
+    uint64_t *full, *empty, *acc_full, *acc_empty, *wbar, *wfull, *wempty;
     uint32_t* tmem_slot;
     float* bias;
 };
-__device__ __forceinline__ Smem carve(uint8_t* smem_raw, int w_bytes, int stages) {
+__device__ __forceinline__ Smem carve(uint8_t* smem_raw, int w_res_bytes, int w_ring_bytes, int stages) {
     Smem s;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    s.W = base;
-    s.A = base + w_bytes;                                     // w_bytes is a multiple of 1024
+    s.W = base;                                               // resident K chunks of the weight slice
+    s.WR = base + w_res_bytes;                                // ring for the streamed chunks (all sizes multiples of 1024)
+    s.A = s.WR + w_ring_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s.A + (size_t)stages * kATile);
     s.full = bars; s.empty = bars + kMaxStages; s.acc_full = s.empty + kMaxStages; s.acc_empty = s.acc_full + kMaxNbt;
     s.wbar = s.acc_empty + kMaxNbt;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.wbar + 1);
+    s.wfull = s.wbar + 1; s.wempty = s.wfull + kMaxWst;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.wempty + kMaxWst);
     s.bias = reinterpret_cast<float*>(s.tmem_slot + 2);
     return s;
 }
@@ -212,7 +217,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
     const int nkc = K / 64;
     const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
     constexpr uint32_t stage_bytes = KCH * kATile;             // one ring stage: 128 rows x (KCH * 64) K
-    const Smem sm = carve(smem_raw, nkc * w_chunk_bytes, S * KCH);
+    // The weight slice is resident for its first `kres` K chunks; the remaining `nstream` chunks are re-streamed
+    // every (step, batch tile) through a small ring by a dedicated warp.  They do not depend on the recurrence, so
+    // that stream runs ahead of the step barrier; the K loop consumes the streamed chunks FIRST.
+    const int kres = P.kres, nstream = nkc - kres, WST = P.wst;
+    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * w_chunk_bytes, S * KCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
@@ -227,8 +236,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
         tc::prefetch_tmap(&c.tmW);
         tc::prefetch_tmap(&c.tmA);
         for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], csize); }
-        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], kEpiWarps / NBT); }
+        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], BWD ? kEpiWarps / NBT : kEpiWarps); }
         tc::mbar_init(sm.wbar, 1);
+        for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(sm.tmem_slot, kTmemCols);
@@ -250,8 +260,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
         // instructions): the compiler then keeps the loop state in uniform registers and issues TMA / MMA /
         // commit without per-instruction election loops -- these single-thread loops pace the whole kernel.
         if (tc::elect_one()) {
-            tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(nkc * w_chunk_bytes));
-            for (int kc = 0; kc < nkc; ++kc) {
+            tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(kres * w_chunk_bytes));
+            for (int kc = 0; kc < kres; ++kc) {
                 if (!BWD) {
                     for (int g = 0; g < 3; ++g)
                         tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, sm.wbar, kc * 64, g * H + u0);
@@ -277,13 +287,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
                 for (int bt = 0; bt < NBT; ++bt) {
                     FN_STAMP(i, bt, 0);
                     if (i > 0) {
-                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i) * (kEpiWarps / NBT));
+                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i) * (BWD ? kEpiWarps / NBT : kEpiWarps));
                         FN_STAMP(i, bt, 1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
                     FN_STAMP(i, bt, 2);
-                    int col = 0;
+                    int col = kres * 64;                       // K order: streamed chunks [kres, nkc) first, then [0, kres)
                     for (int j = 0; j < nst; ++j) {
+                        if (j * KCH == nstream) col = 0;
                         const uint32_t fb = full0 + st * 8u, sa = a0 + st * stage_bytes;
                         tc::mbar_wait_u32(empty0 + st * 8u, ph);
                         if (tc::elect_one()) {
@@ -316,6 +327,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
             const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
             const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
             const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
+            const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
+            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+            uint32_t ws = 0, wph = 0;
             const uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4;   // descriptor address units (16 B)
             const bool mc = csize > 1, skip_mma = (P.dbg_flags & 1) != 0;
             const int nst = nkc / KCH;
@@ -327,166 +341,192 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
                     const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
                     uint64_t bd = bdesc0;
                     for (int j = 0; j < nst; ++j) {
+                        const bool streamed = j * KCH < nstream;
+                        // streamed weight chunks of this stage: wait for them, remember their ring slots
+                        uint32_t wslot[KCH];
+                        if (streamed) {
+#pragma unroll
+                            for (int q = 0; q < KCH; ++q) {
+                                tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
+                                wslot[q] = ws;
+                                if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                            }
+                        }
                         tc::mbar_wait_u32(full0 + st * 8u, ph);
                         tc::tc_fence_after();
                         if (j == 0) FN_STAMP(i, bt, 4);
                         const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
                         if (tc::elect_one()) {
-                            if (!skip_mma) {
 #pragma unroll
-                                for (int q = 0; q < KCH; ++q) {
+                            for (int q = 0; q < KCH; ++q) {
+                                const uint64_t bq = streamed ? wdesc0 + (uint64_t)(wslot[q] * b_step) : bd + (uint64_t)(q * b_step);
+                                if (!skip_mma) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k),
-                                                     bd + (uint64_t)(q * b_step + 2 * k), idesc, (uint32_t)((j | q | k) != 0));
+                                        tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bq + (uint64_t)(2 * k), idesc,
+                                                     (uint32_t)((j | q | k) != 0));
                                 }
+                                if (streamed) tc::umma_commit_u32(wempty0 + wslot[q] * 8u);     // weight-ring slot reusable
                             }
                             if (mc) tc::umma_commit_mc_u32(empty0 + st * 8u, cmask);  // frees the slot in every CTA that fills it
                             else tc::umma_commit_u32(empty0 + st * 8u);
                             if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
                         }
                         __syncwarp();
-                        bd += (uint64_t)KCH * b_step;
+                        if (!streamed) bd += (uint64_t)KCH * b_step;
                         if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                     }
                     FN_STAMP(i, bt, 5);
                 }
             }
         }
+    } else if (warp == kWTailWarp) {
+        // ------------------------------- streamed part of the weight slice -----------------------------
+        if (nstream > 0) {
+            const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+            const int n_tilesteps = (BWD ? T : T) * NBT;
+            uint32_t ws = 0, wph = 1;
+            for (int ts = 0; ts < n_tilesteps; ++ts) {
+                for (int pch = 0; pch < nstream; ++pch) {
+                    tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
+                    if (tc::elect_one()) {
+                        const uint32_t dst = wr0 + ws * (uint32_t)w_chunk_bytes, fb = wfull0 + ws * 8u;
+                        const int kcol = (kres + pch) * 64;
+                        tc::mbar_arrive_expect_tx_u32(fb, (uint32_t)w_chunk_bytes);
+                        if (!BWD) {
+#pragma unroll
+                            for (int g = 0; g < 3; ++g) tc::tma_load_2d_u32(dst + g * U * 128, &c.tmW, fb, kcol, g * H + u0);
+                        } else {
+                            tc::tma_load_2d_u32(dst, &c.tmW, fb, kcol, u0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                }
+            }
+        }
     } else {
         // ------------------------------- epilogue warps --------------------------------------------
-        // NBT == 2: warps 2..5 own batch tile 0 and warps 6..9 tile 1 (each thread: one row, all U units);
-        // NBT == 1: the two warp groups split the units of the single tile.  Per-thread work is processed in
-        // register chunks of CH units.
-        constexpr int UT = (NBT == 2) ? U : U / 2;
-        constexpr int CH = UT > 16 ? 16 : UT;
-        constexpr int NCHK = UT / CH;
+        // All 8 warps serve batch tile 0, then tile 1: warp w reads TMEM lane quarter w % 4 (32 batch rows), the
+        // two warp groups split the slice's units; each thread owns (row, UT units) of every tile for the whole
+        // sequence.  The input-side operand of a chain is EITHER the token-embedding gather (bf16 table) or the
+        // dense bf16 stream -- both have gate stride H, so one prefetch path serves both.
+        constexpr int UT = U / 2;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read (warp id % 4)
-        const int grp = (warp - 2) >> 2;
-        const int bt = NBT == 2 ? grp : 0;
-        const int uu0 = NBT == 2 ? 0 : grp * UT; // unit offset inside the slice
-        const int b = bt * 128 + q * 32 + lane;
-        const bool row_ok = b < B;
-        const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bt * N);
-        unsigned* gflag = gbar + bt;
-        uint64_t* accf = &sm.acc_full[bt];
-        uint64_t* acce = &sm.acc_empty[bt];
+        const int uu = ((warp - 2) >> 2) * UT;   // unit offset inside the slice
+        const int u = u0 + uu;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const bool stamp = (threadIdx.x == 64);
 
         if constexpr (!BWD) {
-            float hreg[UT];
+            float hreg[NBT][UT];
+            int id_next[NBT];
             // time-invariant part of the gate pre-activations -> TMEM columns [kAccCols + bt*N, +N)
 #pragma unroll
-            for (int ch = 0; ch < NCHK; ++ch) {
-                const int uu = uu0 + ch * CH, u = u0 + uu;
-                float pr[CH], pz[CH], pn[CH], h0v[CH];
+            for (int bt = 0; bt < NBT; ++bt) {
+                const int b = bt * 128 + q * 32 + lane;
+                const bool row_ok = b < B;
+                float pr[UT], pz[UT], pn[UT];
 #pragma unroll
-                for (int j = 0; j < CH; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; h0v[j] = 0.f; }
+                for (int j = 0; j < UT; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; hreg[bt][j] = 0.f; }
                 if (row_ok) {
                     if (c.proj) {
                         const float* pj = c.proj + (long long)b * c.proj_ld + u;
-                        ldf<CH>(pj, pr); ldf<CH>(pj + H, pz); ldf<CH>(pj + 2 * H, pn);
+                        ldf<UT>(pj, pr); ldf<UT>(pj + H, pz); ldf<UT>(pj + 2 * H, pn);
                     }
-                    uint32_t hw[CH / 2];
-                    ldb_raw<CH>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
-                    unpack<CH>(hw, h0v);
+                    uint32_t hw[UT / 2];
+                    ldb_raw<UT>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
+                    unpack<UT>(hw, hreg[bt]);
                 }
 #pragma unroll
-                for (int j = 0; j < CH; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[U + uu + j]; hreg[ch * CH + j] = h0v[j]; }
-                const uint32_t tp = t_acc + kAccCols;
-                tmem_st<CH>(tp + uu, pr); tmem_st<CH>(tp + U + uu, pz); tmem_st<CH>(tp + 2 * U + uu, pn);
+                for (int j = 0; j < UT; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[U + uu + j]; }
+                const uint32_t tp = tmem_base + lane_sel + kAccCols + (uint32_t)(bt * N);
+                tmem_st<UT>(tp + uu, pr); tmem_st<UT>(tp + U + uu, pz); tmem_st<UT>(tp + 2 * U + uu, pn);
+                id_next[bt] = (c.emb && row_ok) ? c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b] : 0;
             }
             tmem_st_wait();
+            const bool has_in = (c.emb != nullptr) || (c.dense != nullptr);
 
-            int id_next = (c.emb && row_ok) ? c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b] : 0;
             for (int s = 0; s < T; ++s) {
                 const int tau = c.reverse ? T - 1 - s : s;
                 const int tau_n = c.reverse ? tau - 1 : tau + 1;
-                const long long row_in = (long long)tau * B + b;           // input side is indexed by time
-                const float* e = c.emb + (long long)id_next * 3 * H + u0 + uu0;
-                const __nv_bfloat16* dp = c.dense + row_in * 3 * H + u0 + uu0;
-                // ---- operands that do not depend on the recurrence: fetch (chunk 0) before waiting for the MMA
-                float er[CH], ez[CH], en[CH];
-                uint32_t dr[CH / 2], dz[CH / 2], dn[CH / 2];
-                auto fetch = [&](int ch) {
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) { er[j] = 0.f; ez[j] = 0.f; en[j] = 0.f; }
-                    if (row_ok && c.emb) { ldf<CH>(e + ch * CH, er); ldf<CH>(e + H + ch * CH, ez); ldf<CH>(e + 2 * H + ch * CH, en); }
-                    if (row_ok && c.dense) {
-                        ldb_raw<CH>(dp + ch * CH, dr, false); ldb_raw<CH>(dp + H + ch * CH, dz, false);
-                        ldb_raw<CH>(dp + 2 * H + ch * CH, dn, false);
+                for (int bt = 0; bt < NBT; ++bt) {
+                    const int b = bt * 128 + q * 32 + lane;
+                    const bool row_ok = b < B;
+                    const long long row_in = (long long)tau * B + b;       // input side is indexed by time
+                    // ---- operand that does not depend on the recurrence: fetch before waiting for the MMA
+                    uint32_t ir[UT / 2], iz[UT / 2], in_[UT / 2];
+#pragma unroll
+                    for (int j = 0; j < UT / 2; ++j) { ir[j] = 0u; iz[j] = 0u; in_[j] = 0u; }
+                    if (row_ok && has_in) {
+                        const __nv_bfloat16* src = c.emb ? c.emb + (long long)id_next[bt] * 3 * H + u : c.dense + row_in * 3 * H + u;
+                        ldb_raw<UT>(src, ir, false); ldb_raw<UT>(src + H, iz, false); ldb_raw<UT>(src + 2 * H, in_, false);
+                        if (c.emb && s + 1 < T) id_next[bt] = c.ids[(long long)tau_n * B + b];
                     }
-                };
-                fetch(0);
-                if (row_ok && c.emb && s + 1 < T) id_next = c.ids[(long long)tau_n * B + b];
-                if (stamp) FN_STAMP(s, bt, 6);
-                tc::mbar_wait_warp(accf, s & 1);
-                tc::tc_fence_after();
-                if (stamp) FN_STAMP(s, bt, 7);
-                float r[CH], z[CH], n[CH], g[CH];
+                    if (stamp) FN_STAMP(s, bt, 6);
+                    tc::mbar_wait_warp(&sm.acc_full[bt], s & 1);
+                    tc::tc_fence_after();
+                    if (stamp) FN_STAMP(s, bt, 7);
+                    const uint32_t ta = tmem_base + lane_sel + (uint32_t)(bt * N) + uu;
+                    const uint32_t tp = ta + kAccCols;
+                    float a[UT], p[UT], x[UT], r[UT], z[UT], n[UT], g[UT];
+                    tmem_ld<UT>(ta, a); tmem_ld<UT>(tp, p);
+                    unpack<UT>(ir, x);
 #pragma unroll
-                for (int ch = 0; ch < NCHK; ++ch) {
-                    const int uu = uu0 + ch * CH, u = u0 + uu;
-                    if (ch > 0) fetch(ch);
-                    const uint32_t ta = t_acc + uu, tp = ta + kAccCols;
-                    float a[CH], p[CH];
-                    tmem_ld<CH>(ta, a); tmem_ld<CH>(tp, p);
-                    if (c.dense) { float t[CH]; unpack<CH>(dr, t);
+                    for (int j = 0; j < UT; ++j) r[j] = fast_sigmoid(a[j] + p[j] + x[j]);
+                    tmem_ld<UT>(ta + U, a); tmem_ld<UT>(tp + U, p);
+                    unpack<UT>(iz, x);
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) er[j] += t[j]; }
+                    for (int j = 0; j < UT; ++j) z[j] = fast_sigmoid(a[j] + p[j] + x[j]);
+                    tmem_ld<UT>(ta + 2 * U, a); tmem_ld<UT>(tp + 2 * U, p);
+                    // accumulator consumed: the tensor core may start the next step of this tile
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&sm.acc_empty[bt]);
+                    unpack<UT>(in_, x);
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) r[j] = fast_sigmoid(a[j] + p[j] + er[j]);
-                    tmem_ld<CH>(ta + U, a); tmem_ld<CH>(tp + U, p);
-                    if (c.dense) { float t[CH]; unpack<CH>(dz, t);
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) ez[j] += t[j]; }
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) z[j] = fast_sigmoid(a[j] + p[j] + ez[j]);
-                    tmem_ld<CH>(ta + 2 * U, a); tmem_ld<CH>(tp + 2 * U, p);
-                    if (ch == NCHK - 1) {
-                        // accumulator consumed: the tensor core may start the next step of this tile
-                        tc::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(acce);
-                    }
-                    if (c.dense) { float t[CH]; unpack<CH>(dn, t);
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) en[j] += t[j]; }
-                    float hn[CH];
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) {
+                    for (int j = 0; j < UT; ++j) {
                         g[j] = a[j] + sm.bias[2 * U + uu + j];
-                        n[j] = fast_tanh(p[j] + en[j] + r[j] * g[j]);
-                        hn[j] = (1.f - z[j]) * n[j] + z[j] * hreg[ch * CH + j];
-                        hreg[ch * CH + j] = hn[j];
+                        n[j] = fast_tanh(p[j] + x[j] + r[j] * g[j]);
+                        hreg[bt][j] = (1.f - z[j]) * n[j] + z[j] * hreg[bt][j];
                     }
+                    if (row_ok) stb<UT>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hreg[bt]);
+                    if (stamp) FN_STAMP(s, bt, 9);
+                    if (s + 1 < T) publish(gbar + bt);               // the next step only needs the state
+                    if (stamp) FN_STAMP(s, bt, 10);
                     if (row_ok) {
-                        stb<CH>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hn);
-                        if (NCHK > 1 && c.gates) {       // several chunks: save the gates right away
+                        if (c.gates) {                               // off the critical path: after the publish
                             __nv_bfloat16* gsv = c.gates + row_in * 4 * H + u;
-                            stb<CH>(gsv, r); stb<CH>(gsv + H, z); stb<CH>(gsv + 2 * H, n); stb<CH>(gsv + 3 * H, g);
+                            stb<UT>(gsv, r); stb<UT>(gsv + H, z); stb<UT>(gsv + 2 * H, n); stb<UT>(gsv + 3 * H, g);
                         }
-                    }
-                }
-                if (stamp) FN_STAMP(s, bt, 9);
-                if (s + 1 < T) publish(gflag);                  // the next step only needs the state
-                if (stamp) FN_STAMP(s, bt, 10);
-                if (row_ok) {
-                    if (NCHK == 1 && c.gates) {                 // off the critical path: after the publish
-                        __nv_bfloat16* gsv = c.gates + row_in * 4 * H + u0 + uu0;
-                        stb<CH>(gsv, r); stb<CH>(gsv + H, z); stb<CH>(gsv + 2 * H, n); stb<CH>(gsv + 3 * H, g);
-                    }
-                    if (s == T - 1 && c.h_final) {              // caller-chosen offset / pitch: no alignment assumed
-                        float* hf = c.h_final + (long long)b * c.h_final_ld + u0 + uu0;
+                        if (s == T - 1 && c.h_final) {               // caller-chosen offset / pitch: no alignment assumed
+                            float* hf = c.h_final + (long long)b * c.h_final_ld + u;
 #pragma unroll
-                        for (int j = 0; j < UT; ++j) hf[j] = hreg[j];
+                            for (int j = 0; j < UT; ++j) hf[j] = hreg[bt][j];
+                        }
                     }
                 }
             }
         } else {
-            float carry[UT];
+            // Backward: the epilogue is load-heavy (saved gates, states, incoming gradients), so the two warp groups
+            // each OWN one batch tile (all U units of a row per thread, in register chunks of CH) and run
+            // concurrently instead of serving the tiles one after the other.
+            constexpr int UB = (NBT == 2) ? U : U / 2;
+            constexpr int CH = UB > 16 ? 16 : UB;
+            constexpr int NCHK = UB / CH;
+            const int grp = (warp - 2) >> 2;
+            const int bt = NBT == 2 ? grp : 0;
+            const int uu0 = NBT == 2 ? 0 : grp * UB;
+            const int b = bt * 128 + q * 32 + lane;
+            const bool row_ok = b < B;
+            const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(bt * N);
+            unsigned* gflag = gbar + bt;
+            uint64_t* accf = &sm.acc_full[bt];
+            uint64_t* acce = &sm.acc_empty[bt];
+            float carry[UB];
 #pragma unroll
-            for (int j = 0; j < UT; ++j) carry[j] = 0.f;
+            for (int j = 0; j < UB; ++j) carry[j] = 0.f;
             for (int i = 0; i <= T; ++i) {
                 const int s = T - 1 - i;
                 const int tau = c.reverse ? T - 1 - s : s;
@@ -495,26 +535,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
                 uint32_t wr[CH / 2], wz[CH / 2], wn[CH / 2], wg[CH / 2], wh[CH / 2];
                 float din[CH];
                 auto fetch = [&](int ch) {
-                    const int u = u0 + uu0 + ch * CH;
+                    const int uc = u0 + uu0 + ch * CH;
 #pragma unroll
                     for (int j = 0; j < CH / 2; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
 #pragma unroll
                     for (int j = 0; j < CH; ++j) din[j] = 0.f;
                     if (row_ok && s >= 0) {
-                        const __nv_bfloat16* gsv = c.gates + row * 4 * H + u;
+                        const __nv_bfloat16* gsv = c.gates + row * 4 * H + uc;
                         ldb_raw<CH>(gsv, wr, false); ldb_raw<CH>(gsv + H, wz, false);
                         ldb_raw<CH>(gsv + 2 * H, wn, false); ldb_raw<CH>(gsv + 3 * H, wg, false);
-                        ldb_raw<CH>(c.hsx + (row + (c.reverse ? B : 0)) * H + u, wh, false);   // the state before step s
+                        ldb_raw<CH>(c.hsx + (row + (c.reverse ? B : 0)) * H + uc, wh, false);   // the state before step s
                         if (c.dhs) {
-                            if (c.dhs_f32) ldf<CH>(reinterpret_cast<const float*>(c.dhs) + row * H + u, din);
+                            if (c.dhs_f32) ldf<CH>(reinterpret_cast<const float*>(c.dhs) + row * H + uc, din);
                             else {
                                 uint32_t wd[CH / 2];
-                                ldb_raw<CH>(reinterpret_cast<const __nv_bfloat16*>(c.dhs) + row * H + u, wd, false);
+                                ldb_raw<CH>(reinterpret_cast<const __nv_bfloat16*>(c.dhs) + row * H + uc, wd, false);
                                 unpack<CH>(wd, din);
                             }
                         }
                         if (s == T - 1 && c.dh_final) {
-                            const float* df = c.dh_final + (long long)b * c.dh_final_ld + u;
+                            const float* df = c.dh_final + (long long)b * c.dh_final_ld + uc;
 #pragma unroll
                             for (int j = 0; j < CH; ++j) din[j] += __ldg(df + j);
                         }
@@ -528,11 +568,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
                 float o_i[CH];
 #pragma unroll
                 for (int ch = 0; ch < NCHK; ++ch) {
-                    const int uu = uu0 + ch * CH, u = u0 + uu;
+                    const int uc = u0 + uu0 + ch * CH;
                     if (ch > 0) fetch(ch);
                     float dh[CH];
                     if (i > 0) {
-                        tmem_ld<CH>(t_acc + uu, dh);
+                        tmem_ld<CH>(t_acc + uu0 + ch * CH, dh);
                         if (ch == NCHK - 1) {
                             tc::tc_fence_before();
                             __syncwarp();
@@ -545,7 +585,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < CH; ++j) dh[j] += carry[ch * CH + j] + din[j];
                     if (s < 0) {
-                        if (row_ok) stf<CH>(c.dh0 + (long long)b * H + u, dh);
+                        if (row_ok) stf<CH>(c.dh0 + (long long)b * H + uc, dh);
                         continue;
                     }
                     float r[CH], z[CH], n[CH], g[CH], hp[CH], o_r[CH], o_z[CH], o_n[CH];
@@ -560,7 +600,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
                         carry[ch * CH + j] = dh[j] * z[j];
                     }
                     if (row_ok) {
-                        __nv_bfloat16* dgp = c.dg + row * 4 * H + u;
+                        __nv_bfloat16* dgp = c.dg + row * 4 * H + uc;
                         stb<CH>(dgp, o_r); stb<CH>(dgp + H, o_z); stb<CH>(dgp + 3 * H, o_n);
                         if (NCHK > 1) stb<CH>(dgp + 2 * H, o_i);
                     }
@@ -584,15 +624,50 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
 long long* g_dbg = nullptr;
 constexpr size_t kSmemTail = 1024 /*align*/ + 512 /*barriers*/ + 3 * 64 * 4 /*bias*/;
 
-size_t tc_w_bytes(int U, int H, bool bwd) { return (size_t)((bwd ? 3 * H : H) / 64) * (bwd ? U : 3 * U) * 128; }
-// K chunks (of 64) per ring stage: 2 whenever the chunk count is even (amortises the per-stage barrier work)
-int tc_kch(int H, bool bwd) { return (((bwd ? 3 * H : H) / 64) % 2 == 0) ? 2 : 1; }
-// ring depth in 16 KB tiles
-int tc_stages(int U, int H, bool bwd) {
-    const long long room = (long long)fn_max_smem_optin() - (long long)tc_w_bytes(U, H, bwd) - (long long)kSmemTail;
-    long long s = room / kATile;
-    if (s > kMaxStages) s = kMaxStages;
-    return (int)s;
+// Shared-memory plan of one kernel instance: how many K chunks of the weight slice stay resident, the ring
+// that re-streams the others, and the state-slab ring.
+struct TcPlan {
+    int kch;        // K chunks (of 64) per state-ring stage
+    int stages;     // state-ring stages (kch * 16 KB each)
+    int kres;       // resident weight chunks (of nkc)
+    int wst;        // weight-ring slots (0: everything resident)
+    size_t smem;    // dynamic shared memory bytes
+    bool ok;
+};
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+TcPlan tc_plan(int U, int H, bool bwd) {
+    TcPlan pl{};
+    const int N = bwd ? U : 3 * U, nkc = (bwd ? 3 * H : H) / 64;
+    const long long w_chunk = (long long)N * 128;
+    const long long budget = (long long)fn_max_smem_optin() - (long long)kSmemTail;
+    static const int min_ring_kb = env_int("FN_GRU_RING_KB", 96);      // state ring when the weights do not all fit
+    static const int wring_kb = env_int("FN_GRU_WRING_KB", 32);
+    pl.kch = (nkc % 2 == 0) ? 2 : 1;
+    long long room = budget - nkc * w_chunk;                            // ring space with a fully resident slice
+    if (room >= 6LL * kATile) {
+        pl.kres = nkc; pl.wst = 0;
+    } else {
+        // keep as much of the slice resident as leaves a >= min_ring_kb state ring + a small weight ring
+        int wst = (int)((wring_kb * 1024LL + w_chunk - 1) / w_chunk);
+        if (wst < 2) wst = 2;
+        if (wst > kMaxWst) wst = kMaxWst;
+        long long kres = (budget - min_ring_kb * 1024LL - wst * w_chunk) / w_chunk;
+        if (kres > nkc - pl.kch) kres = nkc - pl.kch;
+        kres -= kres % pl.kch;                                          // streamed / resident parts in whole stages
+        if (kres < 0) { pl.ok = false; return pl; }
+        pl.kres = (int)kres; pl.wst = wst;
+        if (pl.wst < pl.kch) pl.wst = pl.kch;
+        room = budget - kres * w_chunk - pl.wst * w_chunk;
+    }
+    long long tiles = room / kATile;                                    // 16 KB tiles available to the state ring
+    if (tiles < 4) pl.kch = 1;
+    if (tiles > kMaxStages * pl.kch) tiles = kMaxStages * pl.kch;
+    pl.stages = (int)(tiles / pl.kch);
+    if (pl.stages > kMaxStages) pl.stages = kMaxStages;
+    pl.ok = pl.stages >= 2;
+    pl.smem = (size_t)(pl.kres * w_chunk + pl.wst * w_chunk + (long long)pl.stages * pl.kch * kATile) + kSmemTail;
+    return pl;
 }
 
 int fn_make_tmap_bf16_3d(CUtensorMap* out, const void* base, unsigned long long d2, unsigned long long d1,
@@ -611,28 +686,23 @@ int fn_make_tmap_bf16_3d(CUtensorMap* out, const void* base, unsigned long long 
     return FN_OK;
 }
 
-// U for a launch of n_chains chains: the widest slice (least re-streaming of the state slab per FLOP)
-// that still leaves >= 2 ring stages and fits the grid on the machine.
-int pick_u_tc(int n_chains, int H, bool bwd) {
+// U for a launch of n_chains chains: the widest slice that fits the grid on the machine -- the streamed state
+// slab is re-read by every slice of a chain, so fewer, wider slices mean less traffic per FLOP and bigger MMAs.
+int pick_u_tc(int n_chains, int H) {
     const int sms = fn_num_sms();
-    // the state slab is streamed through a ring whose depth (not L2 bandwidth) bounds the step: Little's law,
-    // bytes in flight / TMA round trip.  Prefer the slice width that leaves >= 6 stages.
-    static const int force_u = getenv("FN_GRU_U") ? atoi(getenv("FN_GRU_U")) : 0;
-    for (int pass = 0; pass < 2; ++pass)
+    static const int force_u = env_int("FN_GRU_U", 0);
     for (int U : {32, 16}) {
         if (force_u && U != force_u) continue;
         if (H % U) continue;
-        if (tc_stages(U, H, false) < (pass == 0 ? 6 : 2) || tc_stages(U, H, true) < (pass == 0 ? 6 : 2)) continue;
+        if (!tc_plan(U, H, false).ok || !tc_plan(U, H, true).ok) continue;
         if ((long long)n_chains * (H / U) > sms) continue;
         return U;
     }
-    (void)bwd;
     return 0;
 }
 
 template <int U, int NBT, bool BWD, int KCH>
-int launch_tc(const TcLaunch& P, cudaStream_t st) {
-    const size_t smem = tc_w_bytes(U, P.H, BWD) + (size_t)P.stages * KCH * kATile + kSmemTail;
+int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
     const void* fn = (const void*)gru_tc_kernel<U, NBT, BWD, KCH>;
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
@@ -665,13 +735,13 @@ int launch_tc(const TcLaunch& P, cudaStream_t st) {
     return FN_OK;
 }
 template <bool BWD, int KCH>
-int dispatch_tc2(int U, int nbt, const TcLaunch& P, cudaStream_t st) {
-    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD, KCH>(P, st) : launch_tc<32, 2, BWD, KCH>(P, st);
-    return nbt == 1 ? launch_tc<16, 1, BWD, KCH>(P, st) : launch_tc<16, 2, BWD, KCH>(P, st);
+int dispatch_tc2(int U, int nbt, const TcLaunch& P, size_t smem, cudaStream_t st) {
+    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD, KCH>(P, smem, st) : launch_tc<32, 2, BWD, KCH>(P, smem, st);
+    return nbt == 1 ? launch_tc<16, 1, BWD, KCH>(P, smem, st) : launch_tc<16, 2, BWD, KCH>(P, smem, st);
 }
 template <bool BWD>
-int dispatch_tc(int U, int nbt, int kch, const TcLaunch& P, cudaStream_t st) {
-    return kch == 2 ? dispatch_tc2<BWD, 2>(U, nbt, P, st) : dispatch_tc2<BWD, 1>(U, nbt, P, st);
+int dispatch_tc(int U, int nbt, int kch, const TcLaunch& P, size_t smem, cudaStream_t st) {
+    return kch == 2 ? dispatch_tc2<BWD, 2>(U, nbt, P, smem, st) : dispatch_tc2<BWD, 1>(U, nbt, P, smem, st);
 }
 
 int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
@@ -688,12 +758,12 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
     while (done < n_chains) {
         int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc, U = 0;
         for (; group >= 1; --group)
-            if ((U = pick_u_tc(group, H, bwd)) != 0) break;
+            if ((U = pick_u_tc(group, H)) != 0) break;
         FN_REQUIRE(group >= 1, "fn_gru_seq_bf16: H=%d not supported by the tcgen05 path", H);
         TcLaunch P;
         memset(&P, 0, sizeof(P));
         // cluster of consecutive slices that share (multicast) the streamed state tiles
-        int cs = force_cs ? force_cs : 4;
+        int cs = force_cs ? force_cs : 1;     // multicast sharing measured neutral on B200 (delivery to the SM, not L2 reads, is the bound): off by default
         while (cs > 1 && ((H / U) % cs != 0 || 128 % cs != 0)) cs >>= 1;
         P.cluster = cs;
         for (int i = 0; i < group; ++i) {
@@ -704,6 +774,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
             if (!bwd) {
                 FN_REQUIRE(s.w_hh && s.b_hh, "fn_gru_seq_fwd_bf16: chain %d misses weights", done + i);
                 FN_REQUIRE(!s.emb || s.ids, "fn_gru_seq_fwd_bf16: chain %d has emb without ids", done + i);
+                FN_REQUIRE(!(s.emb && s.dense), "fn_gru_seq_fwd_bf16: chain %d has both a token and a dense input", done + i);
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh, 3ull * H, H, H, U, 64);
                 if (rc) return rc;
                 rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, H, H, 128 / cs, 64);
@@ -715,7 +786,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
                 rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, 4ull * H, 4ull * H, 128 / cs, 64);
                 if (rc) return rc;
             }
-            d.b_hh = s.b_hh; d.emb = s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
+            d.b_hh = s.b_hh; d.emb = (const __nv_bfloat16*)s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
             d.dense = (const __nv_bfloat16*)s.dense;
             d.hsx = (__nv_bfloat16*)s.hsx; d.gates = (__nv_bfloat16*)s.gates;
             d.h_final = s.h_final; d.h_final_ld = s.h_final_ld;
@@ -725,12 +796,13 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
         P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H;
-        const int kch = tc_stages(U, H, bwd) >= 4 ? tc_kch(H, bwd) : 1;
-        P.stages = tc_stages(U, H, bwd) / kch;               // in units of (kch * 16 KB) stages
+        const TcPlan pl = tc_plan(U, H, bwd);
+        const int kch = pl.kch;
+        P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
         P.dbg = g_dbg;
         static const int dbg_flags = getenv("FN_GRU_DBGFLAGS") ? atoi(getenv("FN_GRU_DBGFLAGS")) : 0;
         P.dbg_flags = dbg_flags;
-        const int rc = bwd ? dispatch_tc<true>(U, nbt, kch, P, st) : dispatch_tc<false>(U, nbt, kch, P, st);
+        const int rc = bwd ? dispatch_tc<true>(U, nbt, kch, P, pl.smem, st) : dispatch_tc<false>(U, nbt, kch, P, pl.smem, st);
         if (rc != FN_OK) return rc;
         done += group;
     }

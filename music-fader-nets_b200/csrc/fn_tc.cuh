@@ -105,6 +105,12 @@ __device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

@@ -24,6 +24,8 @@ struct GemmParams {
     long long ldc;
     int M, N, K;
     int a_mn, b_mn, c_bf16, accumulate;
+    int splits, kb_per_split;      // split-K: grid.z CTAs per output tile, each owning kb_per_split K blocks
+    float* partial;                // [splits][M][N] fp32 partial products (splits > 1), reduced by splitk_reduce_kernel
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -37,7 +39,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int nkb = (p.K + BK - 1) / BK;
+    const int nkb_total = (p.K + BK - 1) / BK;
+    const int kb_first = blockIdx.z * p.kb_per_split;
+    const int nkb = max(0, min(p.kb_per_split, nkb_total - kb_first));   // K blocks of this split
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmA);
@@ -53,55 +57,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                tc::mbar_wait(&empty[s], ph ^ 1);                      // slot free (passes immediately on first lap)
-                uint8_t* sa = smem + s * kStageBytes;
+        // control warps run converged; one elected lane issues (see fn_gru_tc.cu)
+        const uint32_t full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty), s0 = tc::smem_u32(smem);
+        uint32_t st = 0, ph = 1;
+        for (int kb = 0; kb < nkb; ++kb) {
+            tc::mbar_wait_u32(empty0 + st * 8u, ph);                   // slot free (passes immediately on first lap)
+            if (tc::elect_one()) {
+                uint8_t* sa = smem + st * kStageBytes;
                 uint8_t* sb = sa + kTileBytes;
-                tc::mbar_arrive_expect_tx(&full[s], kStageBytes);
-                const int k0 = kb * BK;
+                uint64_t* fb = &full[st];
+                tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, kStageBytes);
+                const int k0 = (kb_first + kb) * BK;
                 if (!p.a_mn) {
-                    tc::tma_load_2d(sa, &tmA, &full[s], k0, m0);                       // box 64(K) x 128(M)
+                    tc::tma_load_2d(sa, &tmA, fb, k0, m0);                             // box 64(K) x 128(M)
                 } else {
-                    tc::tma_load_2d(sa, &tmA, &full[s], m0, k0);                       // box 64(M) x 64(K)
-                    tc::tma_load_2d(sa + kTileBytes / 2, &tmA, &full[s], m0 + 64, k0);
+                    tc::tma_load_2d(sa, &tmA, fb, m0, k0);                             // box 64(M) x 64(K)
+                    tc::tma_load_2d(sa + kTileBytes / 2, &tmA, fb, m0 + 64, k0);
                 }
                 if (!p.b_mn) {
-                    tc::tma_load_2d(sb, &tmB, &full[s], k0, n0);
+                    tc::tma_load_2d(sb, &tmB, fb, k0, n0);
                 } else {
-                    tc::tma_load_2d(sb, &tmB, &full[s], n0, k0);
-                    tc::tma_load_2d(sb + kTileBytes / 2, &tmB, &full[s], n0 + 64, k0);
+                    tc::tma_load_2d(sb, &tmB, fb, n0, k0);
+                    tc::tma_load_2d(sb + kTileBytes / 2, &tmB, fb, n0 + 64, k0);
                 }
             }
+            __syncwarp();
+            if (++st == kStages) { st = 0; ph ^= 1u; }
         }
+        (void)s0;
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                tc::mbar_wait(&full[s], ph);
-                tc::tc_fence_after();
-                const uint32_t sa = tc::smem_u32(smem + s * kStageBytes), sb = sa + kTileBytes;
+        const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+        const uint32_t full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty), s0 = tc::smem_u32(smem);
+        // K-major: +32 B inside the swizzle atom per 16 K-elements;  MN-major: +2 groups of 8 K-rows (2048 B)
+        const uint64_t da0 = p.a_mn ? tc::make_sdesc(s0, kTileBytes / 2, 1024) : tc::make_sdesc(s0, 16, 1024);
+        const uint64_t db0 = p.b_mn ? tc::make_sdesc(s0 + kTileBytes, kTileBytes / 2, 1024) : tc::make_sdesc(s0 + kTileBytes, 16, 1024);
+        const uint32_t ka = p.a_mn ? (2048u >> 4) : (32u >> 4), kbs = p.b_mn ? (2048u >> 4) : (32u >> 4);
+        uint32_t st = 0, ph = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            tc::mbar_wait_u32(full0 + st * 8u, ph);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint64_t da = da0 + (uint64_t)(st * (kStageBytes >> 4)), db = db0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // K-major: +32 B inside the swizzle atom per 16 K-elements;  MN-major: +2 groups of 8 K-rows
-                    const uint64_t da = p.a_mn ? tc::make_sdesc(sa + k * 2048, kTileBytes / 2, 1024)
-                                               : tc::make_sdesc(sa + k * 32, 16, 1024);
-                    const uint64_t db = p.b_mn ? tc::make_sdesc(sb + k * 2048, kTileBytes / 2, 1024)
-                                               : tc::make_sdesc(sb + k * 32, 16, 1024);
-                    tc::umma_f16(tmem_base, da, db, idesc, (kb | k) != 0);
-                }
-                tc::umma_commit(&empty[s]);                           // frees the smem slot when these MMAs retire
+                for (int k = 0; k < BK / 16; ++k)
+                    tc::umma_f16(tmem_base, da + (uint64_t)(k * ka), db + (uint64_t)(k * kbs), idesc, (uint32_t)((kb | k) != 0));
+                tc::umma_commit_u32(empty0 + st * 8u);                 // frees the smem slot when these MMAs retire
+                if (kb == nkb - 1) tc::umma_commit(acc_full);          // accumulator complete
             }
-            tc::umma_commit(acc_full);                                // accumulator complete
+            __syncwarp();
+            if (++st == kStages) { st = 0; ph ^= 1u; }
         }
+        if (nkb == 0 && tc::elect_one()) tc::mbar_arrive(acc_full);
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
-        tc::mbar_wait(acc_full, 0);
+        tc::mbar_wait_warp(acc_full, 0);
         tc::tc_fence_after();
         const int row = m0 + q * 32 + lane;
 #pragma unroll 1
@@ -115,15 +125,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                if (p.c_bf16) {
-                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+                if (p.splits > 1) {
+                    float* prow = p.partial + ((long long)blockIdx.z * p.M + row) * p.N + col0;
+                    if (((reinterpret_cast<uintptr_t>(prow) & 15) == 0) && (col0 + 32 <= p.N)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col0 + j < p.N) {
-                            float v = __uint_as_float(r[j]);
-                            if (p.bias) v += __ldg(p.bias + col0 + j);
-                            if (p.accumulate) v += __bfloat162float(crow[j]);
-                            crow[j] = __float2bfloat16(v);
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4*>(prow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) prow[j] = __uint_as_float(r[j]);
+                    }
+                } else if (p.c_bf16) {
+                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+                    const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= p.N);
+                    if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
+                            if (p.bias) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
+                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(crow + j);
+                            if (p.accumulate) {
+                                const uint4 o = *dst;
+                                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[2 * e] += __uint_as_float(ow[e] << 16);
+                                    v[2 * e + 1] += __uint_as_float(ow[e] & 0xffff0000u);
+                                }
+                            }
+                            uint32_t w[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                                w[e] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            *dst = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (col0 + j < p.N) {
+                                float v = __uint_as_float(r[j]);
+                                if (p.bias) v += __ldg(p.bias + col0 + j);
+                                if (p.accumulate) v += __bfloat162float(crow[j]);
+                                crow[j] = __float2bfloat16(v);
+                            }
                         }
                     }
                 } else {
@@ -167,6 +221,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// C = (accumulate ? C : 0) + bias + sum_z partial[z]   (fixed summation order: deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, void* C, long long ldc,
+                                     int c_bf16, const float* __restrict__ bias, int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)M * N) return;
+    const int m = (int)(i / N), n = (int)(i % N);
+    float v = bias ? __ldg(bias + n) : 0.f;
+    for (int z = 0; z < splits; ++z) v += partial[(long long)z * M * N + i];
+    if (c_bf16) {
+        __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(C) + (long long)m * ldc + n;
+        if (accumulate) v += __bfloat162float(*c);
+        *c = __float2bfloat16(v);
+    } else {
+        float* c = reinterpret_cast<float*>(C) + (long long)m * ldc + n;
+        if (accumulate) v += *c;
+        *c = v;
+    }
+}
+
 }  // namespace
 
 // ---- host helpers shared by the tensor-core kernels -------------------------------------------------
@@ -200,10 +273,26 @@ int fn_make_tmap_bf16_2d(CUtensorMap* out, const void* base, unsigned long long 
     return FN_OK;
 }
 
+extern "C" size_t fn_tc_gemm_splitk_ws_bytes(int M, int N, int splits) {
+    return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+}
+
 extern "C" int fn_tc_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                                int b_mn_major, void* C, long long ldc, int c_bf16, const float* bias, int M, int N,
                                int K, int accumulate, void* stream) {
+    return fn_tc_gemm_bf16_splitk(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, c_bf16, bias, M, N, K, accumulate, 1,
+                                  nullptr, 0, stream);
+}
+
+extern "C" int fn_tc_gemm_bf16_splitk(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                                      int b_mn_major, void* C, long long ldc, int c_bf16, const float* bias, int M, int N,
+                                      int K, int accumulate, int splits, void* workspace, size_t ws_bytes, void* stream) {
     FN_REQUIRE(A && B && C && M > 0 && N > 0 && K >= 0, "fn_tc_gemm_bf16: bad args");
+    const int nkb_total = (K + BK - 1) / BK;
+    if (splits < 1) splits = 1;
+    if (splits > nkb_total) splits = nkb_total > 0 ? nkb_total : 1;
+    FN_REQUIRE(splits == 1 || (workspace && ws_bytes >= fn_tc_gemm_splitk_ws_bytes(M, N, splits)),
+               "fn_tc_gemm_bf16_splitk: workspace too small for %d splits", splits);
     CUtensorMap tmA, tmB;
     int rc;
     // K-major operand: memory [rows = M|N][cols = K];  MN-major operand: memory [rows = K][cols = M|N]
@@ -211,14 +300,22 @@ extern "C" int fn_tc_gemm_bf16(const void* A, long long lda, int a_mn_major, con
     if (rc) return rc;
     rc = b_mn_major ? fn_make_tmap_bf16_2d(&tmB, B, K, N, ldb, 64, 64) : fn_make_tmap_bf16_2d(&tmB, B, N, K, ldb, 128, 64);
     if (rc) return rc;
-    GemmParams p{C, bias, ldc, M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, c_bf16 ? 1 : 0, accumulate ? 1 : 0};
+    const int kb_per_split = splits > 1 ? (nkb_total + splits - 1) / splits : (nkb_total > 0 ? nkb_total : 1);
+    GemmParams p{C, bias, ldc, M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, c_bf16 ? 1 : 0, accumulate ? 1 : 0,
+                 splits, kb_per_split, reinterpret_cast<float*>(workspace)};
     static bool attr_done = false;
     if (!attr_done) {
         FN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done = true;
     }
-    dim3 grid(fn_cdiv(N, BN), fn_cdiv(M, BM));
+    dim3 grid(fn_cdiv(N, BN), fn_cdiv(M, BM), splits);
     tc_gemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
     FN_LAUNCH_CHECK();
+    if (splits > 1) {
+        const long long n = (long long)M * N;
+        splitk_reduce_kernel<<<fn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(p.partial, splits, M, N, C, ldc, p.c_bf16, bias,
+                                                                               p.accumulate);
+        FN_LAUNCH_CHECK();
+    }
     return FN_OK;
 }

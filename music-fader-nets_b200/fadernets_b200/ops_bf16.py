@@ -42,8 +42,22 @@ def to_bf16_rows(x: torch.Tensor, cols: int):
     return cast_bf16(xf, rows, cols, cols, 1, ld_dst=ld), ld
 
 
+_SM_SLOTS = 2 * 148          # CTA slots of the 128x128-tile kernel on a B200 (2 per SM)
+
+
 def tc_gemm(A, a_off, lda, a_mn, B, b_off, ldb, b_mn, Cm, c_off, ldc, bias, M, N, K, accumulate=False):
-    """C[M][N] (fp32 or bf16 by Cm.dtype) (+)= A * B (+ bias); operand layouts as in fn_tc_gemm_bf16."""
+    """C[M][N] (fp32 or bf16 by Cm.dtype) (+)= A * B (+ bias); operand layouts as in fn_tc_gemm_bf16.
+    Products with few output tiles and a long K (the T*B-row weight gradients) are split along K."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    splits = 1
+    if K >= 8192 and tiles < _SM_SLOTS:
+        splits = max(1, min(32, _SM_SLOTS // tiles, K // 2048))
+    if splits > 1:
+        nb = LIB.call("fn_tc_gemm_splitk_ws_bytes", M, N, splits)
+        ws = torch.empty(nb, dtype=torch.uint8, device=Cm.device)
+        LIB.call("fn_tc_gemm_bf16_splitk", _p(A, a_off), lda, a_mn, _p(B, b_off), ldb, b_mn, _p(Cm, c_off), ldc,
+                 1 if Cm.dtype == BF16 else 0, _p(bias), M, N, K, 1 if accumulate else 0, splits, _p(ws), nb, _st(Cm))
+        return
     LIB.call("fn_tc_gemm_bf16", _p(A, a_off), lda, a_mn, _p(B, b_off), ldb, b_mn, _p(Cm, c_off), ldc,
              1 if Cm.dtype == BF16 else 0, _p(bias), M, N, K, 1 if accumulate else 0, _st(Cm))
 
@@ -145,8 +159,7 @@ class GruGroupBf16Fn(torch.autograd.Function):
             ch.w_hh, ch.b_hh = whb.data_ptr(), b_hh.data_ptr()
             if sp.emb_cols is not None:
                 c0, Vin = sp.emb_cols
-                emb = torch.empty((Vin, K3), dtype=F32, device=dev)
-                LIB.call("fn_transpose_f32", _p(w_ih, c0), In, _p(emb), K3, K3, Vin, 0, _st(emb))
+                emb = cast_bf16(w_ih, Vin, K3, 1, In, off=c0)          # bf16 W_ih[:, c0:c0+Vin]^T : [Vin][3H]
                 ch.emb, ch.ids = emb.data_ptr(), sp.ids.data_ptr()
                 tmp.append(emb)
             if sp.z_cols is not None:

@@ -324,9 +324,9 @@ def test_gru_group_bf16(dev, B, T, H, Vin, Zin):
     D = [t.detach().double().requires_grad_(True) for t in leaves]
     a_wih, a_bih, a_whh, a_bhh, b_wih, b_bih, b_whh, b_bhh, zin_, h0b_, c_wih, c_bih, c_whh, c_bhh, xin_ = D
     idl = ids.long()
-    gi_a = a_wih.t()[idl] + a_bih
+    gi_a = _ste_bf16(a_wih).t()[idl] + a_bih                        # the gathered table is stored in bf16
     ra = _torch_gru_bf16(gi_a, torch.zeros(B, H, dtype=torch.float64, device=dev), a_whh, a_bhh, True)
-    gi_b = b_wih[:, :Vin].t()[idl] + (zin_ @ b_wih[:, Vin:].t() + b_bih)[None]
+    gi_b = _ste_bf16(b_wih[:, :Vin]).t()[idl] + (zin_ @ b_wih[:, Vin:].t() + b_bih)[None]
     rb = _torch_gru_bf16(gi_b, h0b_, b_whh, b_bhh, False)
     gi_c = _ste_bf16(xin_ @ _ste_bf16(c_wih).t() + c_bih)          # the dense stream is stored in bf16
     rc = _torch_gru_bf16(gi_c, xin_[0], c_whh, c_bhh, False)
@@ -399,3 +399,33 @@ def test_linear_bf16(dev, M, N, K):
     assert gx.dtype == bf
     close(gx.float(), rgx, rtol=1e-2, atol=1e-2, what="dx"); close(gw, rgw, rtol=1e-4, atol=1e-3, what="dw")
     close(gb, rgb, rtol=1e-4, atol=1e-3, what="db")
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("c_bf16", [0, 1])
+def test_tc_gemm_splitk(dev, a_mn, b_mn, c_bf16):
+    """Split-K path (workspace partials + fixed-order reduce), ragged K split, bias + accumulate; and twice the
+    same call gives bit-identical results (no float atomics)."""
+    from fadernets_b200._lib import LIB
+    from fadernets_b200.ops import _p, _st
+    bf = torch.bfloat16
+    M, N, K, splits = 304, 200, 5000, 7        # lda = M, ldb = N in the MN-major layouts: multiples of 8
+    A = rnd(M, K, seed=1, dev=dev).to(bf); Bm = rnd(K, N, seed=2, dev=dev).to(bf)
+    Abuf = A.t().contiguous() if a_mn else A.contiguous()              # a_mn: stored [K][M]
+    Bbuf = Bm.contiguous() if b_mn else Bm.t().contiguous()            # b_mn: stored [K][N]; else [N][K]
+    lda = M if a_mn else K
+    ldb = N if b_mn else K
+    bias = rnd(N, seed=3, dev=dev)
+    C0 = rnd(M, N, seed=4, dev=dev)
+    outs = []
+    for rep in range(2):
+        Cm = C0.to(bf) if c_bf16 else C0.clone()
+        nb = LIB.call("fn_tc_gemm_splitk_ws_bytes", M, N, splits)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        LIB.call("fn_tc_gemm_bf16_splitk", _p(Abuf), lda, a_mn, _p(Bbuf), ldb, b_mn, _p(Cm), N, c_bf16, _p(bias), M, N, K, 1,
+                 splits, _p(ws), nb, _st(Cm))
+        torch.cuda.synchronize()
+        outs.append(Cm.clone())
+    assert torch.equal(outs[0], outs[1]), "split-K result is not run-to-run deterministic"
+    ref = (C0.to(bf).double() if c_bf16 else C0.double()) + A.double() @ Bm.double() + bias.double()
+    close(outs[0], ref, rtol=1e-2 if c_bf16 else 2e-5, atol=5e-2 if c_bf16 else 2e-3, what="split-K gemm")
