@@ -32,6 +32,9 @@ WORKLOADS = {
     "c2_bf16": ("gmvae", 64, 256, 512, 128, 2, "bf16"),
     "c3": ("gmvae", 256, 512, 1024, 128, 2, "bf16"),
     "c3_f32": ("gmvae", 256, 512, 1024, 128, 2, "f32"),
+    # BASELINE configs[4]: arousal-transfer inference (encode -> shift z -> greedy decode), seq_len 512
+    "c5": ("gmvae", 256, 512, 1024, 128, 2, "bf16"),
+    "c5_f32": ("gmvae", 64, 512, 512, 128, 2, "f32"),
 }
 STEP0 = 20000          # beta0 = beta = 0.2: every KL term is live
 
@@ -45,6 +48,16 @@ def gru_flops_per_token(H):
     """Recurrent-GEMM share handled by the persistent GRU kernels: 8 chains x 2*3H*H fwd, and the
     dgh*W_hh product of BPTT (same size) -> 2 x 48 H^2."""
     return 2.0 * 48.0 * H * H
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the GRU kernel launches of one step, from the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None if it was not captured."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path)).get(workload)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -249,7 +262,8 @@ def run_ours(args):
                                 "gru_fwd_kernel + gru_bwd_kernel (persistent fp32 SIMT recurrent GEMM + gates)"),
                      "bound": "tensor", "achieved": round(achieved, 3) if achieved else None,
                      "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                     "frac": round(achieved / peaks["tf_sust"], 5) if achieved else None, "traffic": None,
+                     "frac": round(achieved / peaks["tf_sust"], 5) if achieved else None,
+                     "traffic": ncu_traffic(args.workload),
                      "peak_source": peaks["src"] + " cuBLAS bf16 sustained (kernel timed inside a long step)" +
                                     ("" if prec == "bf16" else "; fp32 SIMT exact-parity path (FMA pipe, no tensor cores)"),
                      "flops_per_launch_group": gru_flops, "ms_per_step_in_kernel": round(gru_ms, 3) if gru_ms else None,
@@ -267,6 +281,78 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_decode(args):
+    """BASELINE configs[4]: arousal transfer = encode(x) -> z + lambda * (mu_lookup(1) - mu_lookup(0)) -> eval-mode
+    global_decoder(z, steps=T) (reference arousal_transfer.ipynb cells 11/15/17, test_class.py:233-254).  One
+    "step" = one batch of B sequences; value = sequences/s (replicas only when N > 1: no collective)."""
+    import fadernets_b200 as fn
+    from fadernets_b200._lib import LIB
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    variant, B, T, H, Z, K, prec = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    model = fn.MusicAttrRegGMVAE(342, 3, 16, 24, H, Z, 32, n_component=K).to(dev).eval()
+    model.set_precision(prec)
+    host = make_batch_pinned(B, T, seed=rank)
+    h2d = host[0].numel() * host[0].element_size() + host[3].numel() * host[3].element_size()
+
+    def one(e2e):
+        d = host[0].to(dev, non_blocking=True); c = host[3].to(dev, non_blocking=True)
+        with torch.no_grad():
+            dis_r, dis_n = model.encode(d)                       # token ids are accepted in place of the dense one-hot
+            shift_r = model.mu_r_lookup.weight[1] - model.mu_r_lookup.weight[0]
+            shift_n = model.mu_n_lookup.weight[1] - model.mu_n_lookup.weight[0]
+            z = torch.cat([dis_r.mean + 0.5 * shift_r, dis_n.mean + 0.5 * shift_n, c], 1)
+            _, toks = model.decode_greedy(z, T, return_logp=False)
+        return toks.cpu() if e2e else toks
+
+    def timed(n, e2e):
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        l0 = LIB.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            toks = one(e2e)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / 1e3, LIB.launches - l0, toks
+
+    timed(max(1, min(args.warmup, 2)), False)
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    n = max(1, min(args.steps, 5))
+    sec, launches, toks = timed(n, False)
+    clocks = sampler.stop() if sampler else None
+    sec_e2e, _, _ = timed(n, True)
+    if rank == 0:
+        peaks = measured_peaks()
+        fl = 2.0 * (18.0 * H * H + H * 342) * B * T              # cell 1 + cell 2 (input + recurrent) + projection
+        line = {"metric": "sequences/sec greedy decode (arousal-transfer inference)", "value": round(B * world * n / sec, 2),
+                "unit": "sequences/s", "n_gpus": world, "steps": n, "warmup": max(1, min(args.warmup, 2)),
+                "ms_per_step": round(sec / n * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": prec, "data": "synthetic",
+                "config": {"workload": f"{args.workload}: encode + latent shift + greedy global_decoder, batch {B}/GPU x {T} steps, "
+                                       f"hidden {H}, {prec}", "global_batch": B * world, "seq_len": T, "hidden": H,
+                           "parallelism": f"replicas{world}", "l2": "weights (2 x 3H x H + H x V bf16) stay L2-resident by design"},
+                "e2e": {"value": round(B * world * n / sec_e2e, 2), "unit": "sequences/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": B * T * 8},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": "per-step decode kernels (gate block x2, projections)", "bound": "tensor",
+                             "achieved": round(fl / (sec / n) / 1e12, 3), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                             "frac": round(fl / (sec / n) / 1e12 / peaks["tf_sust"], 5), "traffic": None},
+                "tokens_head": toks[0, :8].tolist()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 def cpu_reference(workload, steps, warmup, sample_batch=None):
     """The reference algorithm on the host cores: the oracle port (oracle/fader_oracle.py, dense one-hot
     GEMMs like the reference's nn.GRU on one-hot input) on a BOUNDED sample of the workload."""
@@ -274,7 +360,7 @@ def cpu_reference(workload, steps, warmup, sample_batch=None):
     variant, B, T, H, Z, K, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = sample_batch or {"c1": 4, "c2": 8, "c2_bf16": 8, "c3": 4, "c3_f32": 4}[workload]
+    Bs = sample_batch or {"c1": 4, "c2": 16, "c2_bf16": 16, "c3": 16, "c3_f32": 16}[workload]
     w = fo.init_weights(H, Z, variant, max(K, 1), seed=0)
     st = fo.AdamState(w)
     batch = fo.synth_batch(Bs, T, seed=0)
@@ -303,8 +389,10 @@ def run_reference(args):
             "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: train step, batch {B}/GPU x seq_len {T}, hidden {H}, z {Z}, K {K}, {prec}",
-                       "seq_len": T, "hidden": H},
+            "config": {"workload": f"{args.workload}: Music{'AttrRegGMVAE' if variant == 'gmvae' else 'AttrRegVAE'} "
+                                   f"train step, batch {B}/GPU x seq_len {T}, hidden {H}, z {Z}, K {K}, {prec}",
+                       "global_batch": B * world, "seq_len": T, "hidden": H, "parallelism": f"dp{world}",
+                       "note": "reference algorithm (fp32, dense one-hot GEMMs) on the host cores; bounded sample, see cpu_baseline.sample"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -315,7 +403,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 (default) = BASELINE configs[2]: the per-GPU shape of the 1/2/4/8-GPU metric (configs[3] = 8 x c3); "
+                         "c2 = configs[1] (fp32 exact-parity path); c1 = configs[0]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add per-C-ABI-call device time to the JSON line")
@@ -325,7 +415,7 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
-        run_ours(args)
+        (run_decode if args.workload.startswith("c5") else run_ours)(args)
 
 
 if __name__ == "__main__":

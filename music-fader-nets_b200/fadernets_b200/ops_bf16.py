@@ -121,6 +121,66 @@ def linear_bf16(x, w, b, out_bf16=False):
     return LinearBf16Fn.apply(x, w, b, out_bf16)
 
 
+def _finish_chain_grads(sp, d, dg, dh0, B, T, H, dxin_done=None):
+    """Parameter / input gradients of one chain from its gate-gradient stream dg [T][B][4H] = (dr, dz, dn, dn*r):
+    returns [dW_ih, db_ih, dW_hh, db_hh, (dz_in), (dxin), (dh0)] in the order of the chain's inputs."""
+    dev = dg.device
+    st = stream_ptr(dev)
+    K3, H4, TB = 3 * H, 4 * H, T * B
+    w_ih, hsx = d["w_ih"], d["hsx"]
+    In = w_ih.shape[1]
+    # ---- recurrent weight: dW_hh = sum_tau dgh_tau^T (state before that step); rows tau*B+b of dg pair
+    # with slab tau (forward chain) / tau+1 (reverse chain) of hsx.  dgh = dg[:, :2H] | dg[:, 3H:].
+    dw_hh = torch.empty((K3, H), dtype=F32, device=dev)
+    hoff = B * H if sp.reverse else 0
+    tc_gemm(dg, 0, H4, 1, hsx, hoff, H, 1, dw_hh, 0, H, None, 2 * H, H, TB)
+    tc_gemm(dg, K3, H4, 1, hsx, hoff, H, 1, dw_hh, 2 * H * H, H, None, H, H, TB)
+    # ---- time sums -> biases and the time-invariant projection
+    dproj = torch.empty((B, K3), dtype=F32, device=dev)
+    dghsum = torch.empty((B, K3), dtype=F32, device=dev)
+    LIB.call("fn_time_sum_bf16", _p(dg), B, T, H, _p(dproj), _p(dghsum), st)
+    db_hh = torch.empty(K3, dtype=F32, device=dev)
+    db_ih = torch.empty(K3, dtype=F32, device=dev)
+    col_sum(dghsum, K3, B, K3, db_hh)
+    col_sum(dproj, K3, B, K3, db_ih)
+    # ---- input weight
+    covered = sum(c[1] for c in (sp.emb_cols, sp.z_cols, sp.x_cols) if c is not None)
+    dw_ih = (torch.empty if covered == In else torch.zeros)((K3, In), dtype=F32, device=dev)
+    dz_in = dxin = None
+    if sp.emb_cols is not None:
+        # autograd of `onehot @ W_ih[:, :Vin]^T`: dW_ih[:, :Vin] = dgi^T onehot, on the tensor cores
+        # (the one-hot operand is exact in bf16)
+        c0, Vin = sp.emb_cols
+        oh = onehot_bf16(sp.ids, Vin)
+        tc_gemm(dg, 0, H4, 1, oh, 0, r8(Vin), 1, dw_ih, c0, In, None, K3, Vin, TB)
+    if sp.z_cols is not None:
+        c0, Zin = sp.z_cols
+        z_in = d["z_in"]
+        gemm(dproj, 0, 1, K3, z_in, 0, Zin, 1, dw_ih, c0, In, None, K3, Zin, B)
+        dz_in = torch.empty((B, Zin), dtype=F32, device=dev)
+        gemm(dproj, 0, K3, 1, w_ih, c0, In, 1, dz_in, 0, Zin, None, B, Zin, K3)
+    if sp.x_cols is not None:
+        c0, Hin = sp.x_cols
+        xin, wib = d["xin"], d["w_ih_b"]
+        if dxin_done is None:
+            dxin = torch.empty((T, B, Hin), dtype=BF16, device=dev)
+            tc_gemm(dg, 0, H4, 0, wib, c0, r8(In), 1, dxin, 0, Hin, None, TB, Hin, K3)
+            if sp.h0 == "xin0":
+                # grad wrt xin[0] also receives the initial-state gradient of this chain
+                LIB.call("fn_add_f32_to_bf16", _p(dxin), _p(dh0), B * Hin, st)
+        else:
+            dxin = dxin_done
+        tc_gemm(dg, 0, H4, 1, xin, 0, Hin, 1, dw_ih, c0, In, None, K3, Hin, TB)
+    out = [dw_ih, db_ih, dw_hh, db_hh]
+    if sp.z_cols is not None:
+        out.append(dz_in)
+    if sp.x_cols is not None:
+        out.append(dxin)
+    if sp.h0 == "tensor":
+        out.append(dh0)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # GRU chains on the tensor cores
 # ------------------------------------------------------------------------------------------------
@@ -248,54 +308,165 @@ class GruGroupBf16Fn(torch.autograd.Function):
 
         out_grads = []
         for ci, sp in enumerate(specs):
-            d, b = keep[ci], bufs[ci]
-            w_ih, hsx, dg = d["w_ih"], d["hsx"], b["dg"]
-            In = w_ih.shape[1]
-            # ---- recurrent weight: dW_hh = sum_tau dgh_tau^T (state before that step); rows tau*B+b of dg pair
-            # with slab tau (forward chain) / tau+1 (reverse chain) of hsx.  dgh = dg[:, :2H] | dg[:, 3H:].
-            dw_hh = torch.empty((K3, H), dtype=F32, device=dev)
-            hoff = B * H if sp.reverse else 0
-            tc_gemm(dg, 0, H4, 1, hsx, hoff, H, 1, dw_hh, 0, H, None, 2 * H, H, TB)
-            tc_gemm(dg, K3, H4, 1, hsx, hoff, H, 1, dw_hh, 2 * H * H, H, None, H, H, TB)
-            # ---- time sums -> biases and the time-invariant projection
-            dproj = torch.empty((B, K3), dtype=F32, device=dev)
-            dghsum = torch.empty((B, K3), dtype=F32, device=dev)
-            LIB.call("fn_time_sum_bf16", _p(dg), B, T, H, _p(dproj), _p(dghsum), st)
-            db_hh = torch.empty(K3, dtype=F32, device=dev)
-            db_ih = torch.empty(K3, dtype=F32, device=dev)
-            col_sum(dghsum, K3, B, K3, db_hh)
-            col_sum(dproj, K3, B, K3, db_ih)
-            # ---- input weight
-            covered = sum(c[1] for c in (sp.emb_cols, sp.z_cols, sp.x_cols) if c is not None)
-            dw_ih = (torch.empty if covered == In else torch.zeros)((K3, In), dtype=F32, device=dev)
-            dz_in = dxin = None
-            if sp.emb_cols is not None:
-                # autograd of `onehot @ W_ih[:, :Vin]^T`: dW_ih[:, :Vin] = dgi^T onehot, on the tensor cores
-                # (the one-hot operand is exact in bf16)
-                c0, Vin = sp.emb_cols
-                oh = onehot_bf16(sp.ids, Vin)
-                tc_gemm(dg, 0, H4, 1, oh, 0, r8(Vin), 1, dw_ih, c0, In, None, K3, Vin, TB)
-            if sp.z_cols is not None:
-                c0, Zin = sp.z_cols
-                z_in = d["z_in"]
-                gemm(dproj, 0, 1, K3, z_in, 0, Zin, 1, dw_ih, c0, In, None, K3, Zin, B)
-                dz_in = torch.empty((B, Zin), dtype=F32, device=dev)
-                gemm(dproj, 0, K3, 1, w_ih, c0, In, 1, dz_in, 0, Zin, None, B, Zin, K3)
-            if sp.x_cols is not None:
-                c0, Hin = sp.x_cols
-                xin, wib = d["xin"], d["w_ih_b"]
-                dxin = torch.empty((T, B, Hin), dtype=BF16, device=dev)
-                tc_gemm(dg, 0, H4, 0, wib, c0, r8(In), 1, dxin, 0, Hin, None, TB, Hin, K3)
-                tc_gemm(dg, 0, H4, 1, xin, 0, Hin, 1, dw_ih, c0, In, None, K3, Hin, TB)
-                if sp.h0 == "xin0":
-                    # grad wrt xin[0] also receives the initial-state gradient of this chain
-                    LIB.call("fn_add_f32_to_bf16", _p(dxin), _p(b["dh0"]), B * Hin, st)
-            out_grads += [dw_ih, db_ih, dw_hh, db_hh]
-            if sp.z_cols is not None:
-                out_grads.append(dz_in)
-            if sp.x_cols is not None:
-                out_grads.append(dxin)
-            if sp.h0 == "tensor":
-                out_grads.append(b["dh0"])
+            out_grads += _finish_chain_grads(sp, keep[ci], bufs[ci]["dg"], bufs[ci]["dh0"], B, T, H)
         ctx.keep = None
         return (None, None, None, None, None) + tuple(out_grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder stack: sub-decoder r, sub-decoder n, global cell 1 and global cell 2 as one wavefront
+# ------------------------------------------------------------------------------------------------
+def _segments(T: int):
+    """Time segments of the wavefront: cell 2 runs one segment behind cell 1 in the same launch."""
+    if T % 4 == 0 and T >= 64:
+        return 4
+    if T % 2 == 0 and T >= 16:
+        return 2
+    return 1
+
+
+class DecoderStackBf16Fn(torch.autograd.Function):
+    """The four decoder recurrences of one forward pass (gmm_model.py:100-149): sub-decoder r, sub-decoder n, global
+    cell 1 (teacher-forced token gather + z projection) and global cell 2 (dense input = cell 1's states, initial
+    state = cell 1's first state).  Cell 2 only depends on cell 1's *earlier* states, so time is cut into S segments
+    and launch k runs {r, n, cell 1} on segment k together with {cell 2} on segment k-1 (its input projection for
+    that segment is one batched tensor-core GEMM in between): S+1 launches of T/S steps instead of 2 of T, and no
+    launch that fills only a quarter of the machine.  Backward mirrors it.
+
+    apply(specs, B, T, H, *tensors): specs = (r, n, g) ChainSpecs (emb + z projection + h0 tensor); tensors = per chain
+    w_ih, b_ih, w_hh, b_hh, z_in, h0 for r, n, g, then w_ih, b_ih, w_hh, b_hh of cell 2.
+    Returns (hs_r, hs_n, hs_g2): bf16 [T,B,H]."""
+
+    @staticmethod
+    def forward(ctx, specs, B: int, T: int, H: int, *tensors):
+        dev = tensors[0].device
+        require_cuda(*tensors)
+        need_grad = any(ctx.needs_input_grad)
+        K3, H4 = 3 * H, 4 * H
+        st = stream_ptr(dev)
+        keep = []
+        for ci, sp in enumerate(specs):
+            w_ih, b_ih, w_hh, b_hh, z_in, h0 = tensors[6 * ci:6 * ci + 6]
+            z_in, h0 = _f32c(z_in), _f32c(h0)
+            In = w_ih.shape[1]
+            c0, Vin = sp.emb_cols
+            zc0, Zin = sp.z_cols
+            d = dict(w_ih=w_ih, w_hh=w_hh, b_hh=b_hh, z_in=z_in, xin=None, spec=sp)
+            d["w_hh_b"] = cast_bf16(w_hh, K3, H, H, 1)
+            d["emb"] = cast_bf16(w_ih, Vin, K3, 1, In, off=c0)
+            proj = torch.empty((B, K3), dtype=F32, device=dev)
+            gemm(z_in, 0, Zin, 1, w_ih, zc0, 1, In, proj, 0, K3, b_ih, B, K3, Zin)
+            d["proj"] = proj
+            hsx = torch.empty((T + 1, B, H), dtype=BF16, device=dev)
+            LIB.call("fn_cast_bf16", _p(h0), H, 1, _p(hsx), H, B, H, st)
+            d["hsx"] = hsx
+            d["gates"] = torch.empty((T, B, H4), dtype=BF16, device=dev) if need_grad else None
+            keep.append(d)
+        w_ih2, b_ih2, w_hh2, b_hh2 = tensors[18:22]
+        g = keep[2]
+        sp2 = ChainSpec(x_cols=(0, H), h0="xin0", want_hs=True)
+        d2 = dict(w_ih=w_ih2, w_hh=w_hh2, b_hh=b_hh2, z_in=None, xin=g["hsx"][1:], spec=sp2)
+        d2["w_hh_b"] = cast_bf16(w_hh2, K3, H, H, 1)
+        d2["w_ih_b"] = cast_bf16(w_ih2, K3, H, H, 1)
+        d2["hsx"] = torch.empty((T + 1, B, H), dtype=BF16, device=dev)
+        d2["gates"] = torch.empty((T, B, H4), dtype=BF16, device=dev) if need_grad else None
+        dense = torch.empty((T, B, K3), dtype=BF16, device=dev)
+        keep.append(d2)
+
+        S = _segments(T)
+        L = T // S
+        bar = torch.empty(64 * 4, dtype=torch.uint8, device=dev)
+        for k in range(S + 1):
+            chains = (FnGruChainBf16 * 4)()
+            n = 0
+            if k < S:
+                t0 = k * L
+                for d in keep[:3]:
+                    ch = chains[n]; n += 1
+                    ch.w_hh, ch.b_hh = d["w_hh_b"].data_ptr(), d["b_hh"].data_ptr()
+                    ch.emb, ch.ids = d["emb"].data_ptr(), d["spec"].ids.data_ptr() + t0 * B * 4
+                    ch.proj, ch.proj_ld = d["proj"].data_ptr(), K3
+                    ch.hsx = d["hsx"].data_ptr() + t0 * B * H * 2
+                    if need_grad:
+                        ch.gates = d["gates"].data_ptr() + t0 * B * H4 * 2
+            if k >= 1:
+                t0 = (k - 1) * L
+                # cell 2's input projection for this segment: dense[t] = hs_g[t] W_ih2^T + b_ih2, hs_g[t] = slab t+1
+                tc_gemm(g["hsx"], (t0 + 1) * B * H, H, 0, d2["w_ih_b"], 0, H, 0, dense, t0 * B * K3, K3, b_ih2, L * B, K3, H)
+                if k == 1:
+                    d2["hsx"][0].copy_(g["hsx"][1])                 # hx[1] <- the new hx[0] at step 0 (gmm_model.py:134-135)
+                ch = chains[n]; n += 1
+                ch.w_hh, ch.b_hh = d2["w_hh_b"].data_ptr(), b_hh2.data_ptr()
+                ch.dense = dense.data_ptr() + t0 * B * K3 * 2
+                ch.hsx = d2["hsx"].data_ptr() + t0 * B * H * 2
+                if need_grad:
+                    ch.gates = d2["gates"].data_ptr() + t0 * B * H4 * 2
+            LIB.call("fn_gru_seq_fwd_bf16", chains, n, B, L, H, _p(bar), bar.numel(), st)
+        for d in keep:
+            d.pop("emb", None); d.pop("proj", None)
+        ctx.keep, ctx.dims, ctx.S = keep, (B, T, H), S
+        return keep[0]["hsx"][1:], keep[1]["hsx"][1:], d2["hsx"][1:]
+
+    @staticmethod
+    def backward(ctx, g_r, g_n, g_2):
+        keep, (B, T, H), S = ctx.keep, ctx.dims, ctx.S
+        dev = keep[0]["hsx"].device
+        K3, H4 = 3 * H, 4 * H
+        L = T // S
+        st = stream_ptr(dev)
+
+        def as_dhs(gr):
+            if gr is None:
+                return None
+            gr = gr if gr.is_contiguous() else gr.contiguous()
+            return gr if gr.dtype in (BF16, F32) else gr.float()
+
+        dhs = [as_dhs(g_r), as_dhs(g_n), torch.empty((T, B, H), dtype=BF16, device=dev), as_dhs(g_2)]
+        whts = [cast_bf16(d["w_hh"], H, K3, 1, H) for d in keep]                     # W_hh^T [H][3H]
+        dgs = [torch.empty((T, B, H4), dtype=BF16, device=dev) for _ in keep]
+        dh0 = [[torch.empty((B, H), dtype=F32, device=dev) for _ in range(2)] for _ in keep]
+        last = [None] * 4                                                             # dh0 of the later segment
+        bar = torch.empty(64 * 4, dtype=torch.uint8, device=dev)
+        d2 = keep[3]
+
+        def fill(ch, ci, j, flip):
+            d = keep[ci]
+            t0 = j * L
+            ch.w_hh_t = whts[ci].data_ptr()
+            ch.hsx = d["hsx"].data_ptr() + t0 * B * H * 2
+            ch.gates = d["gates"].data_ptr() + t0 * B * H4 * 2
+            ch.dg = dgs[ci].data_ptr() + t0 * B * H4 * 2
+            if dhs[ci] is not None:
+                ch.dhs = dhs[ci].data_ptr() + t0 * B * H * dhs[ci].element_size()
+                ch.dhs_f32 = 0 if dhs[ci].dtype == BF16 else 1
+            if last[ci] is not None:                        # gradient wrt the state this segment hands on
+                ch.dh_final, ch.dh_final_ld = last[ci].data_ptr(), H
+            out = dh0[ci][flip]
+            ch.dh0 = out.data_ptr()
+            return out
+
+        for k in range(S + 1):
+            chains = (FnGruChainBf16 * 4)()
+            n = 0
+            new_last = list(last)
+            if k < S:
+                new_last[3] = fill(chains[n], 3, S - 1 - k, k & 1); n += 1
+            if k >= 1:
+                for ci in range(3):
+                    new_last[ci] = fill(chains[n], ci, S - k, k & 1); n += 1
+            LIB.call("fn_gru_seq_bwd_bf16", chains, n, B, L, H, _p(bar), bar.numel(), st)
+            last = new_last
+            if k < S:
+                # gradient wrt cell 1's states of this segment = cell 2's input gradient: dgi W_ih2
+                j = S - 1 - k
+                t0 = j * L
+                tc_gemm(dgs[3], t0 * B * H4, H4, 0, d2["w_ih_b"], 0, H, 1, dhs[2], t0 * B * H, H, None, L * B, H, K3)
+                if j == 0:                                   # ... plus cell 2's initial-state gradient on hs_g[0]
+                    LIB.call("fn_add_f32_to_bf16", _p(dhs[2]), _p(last[3]), B * H, st)
+
+        out_grads = []
+        for ci in range(3):
+            out_grads += _finish_chain_grads(keep[ci]["spec"], keep[ci], dgs[ci], last[ci], B, T, H)
+        out_grads += _finish_chain_grads(d2["spec"], d2, dgs[3], last[3], B, T, H, dxin_done=dhs[2])[:4]
+        ctx.keep = None
+        return (None, None, None, None) + tuple(out_grads)

@@ -53,6 +53,18 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(FnGruChain) == 8 * len(names) - 4 * 0 - 0 or ctypes.sizeof(FnGruChain) % 8 == 0
 
 
+def test_bf16_struct_layout_matches_header():
+    import ctypes
+    from fadernets_b200._lib import FnGruChainBf16
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct FnGruChainBf16 {"):src.index("} FnGruChainBf16;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+)\s*;", body)
+    assert names == [f[0] for f in FnGruChainBf16._fields_]
+    # two int32 share one 8-byte slot; everything else is pointer / long long
+    assert ctypes.sizeof(FnGruChainBf16) == 8 * (len(names) - 1)
+
+
 def test_model_surface_matches_reference_contract():
     import fadernets_b200 as fn
     from oracle import fader_oracle as fo
