@@ -193,6 +193,10 @@ int fn_ids_to_onehot(const int64_t* ids, int B, int T, int V, float* onehot, voi
  * stream (start token at t=0, then ids[:, t-1]; gmm_model.py:120-121,139-142). */
 int fn_ids_to_time_major(const int64_t* ids, int B, int T, int shift, int start_token, int32_t* ids_tm,
                          void* stream);
+/* Post-processing of decoded tokens, batched: clean_output (test_class.py:44-50) keeps, per row of tokens
+ * (rows, steps) int64, the span after trimming leading / trailing zeros and cutting at the first EOS (1):
+ * start[row], len[row] index the original row. */
+int fn_clean_tokens(const int64_t* tokens, int rows, int steps, int32_t* start, int32_t* len, void* stream);
 /* dst[c][r] = src[r][c] (+= if accumulate)  -- W_ih[:, :V] <-> embedding-table layout */
 int fn_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols,
                      int accumulate, void* stream);

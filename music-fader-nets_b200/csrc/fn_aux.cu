@@ -96,6 +96,32 @@ __global__ void transpose_kernel(const float* __restrict__ src, long long ld_src
     }
 }
 
+// clean_output (test_class.py:44-50) per row: trim leading/trailing zeros, cut at the first EOS (1) of what is left.
+// One warp per row; start/len describe the kept span of the ORIGINAL row.
+__global__ void clean_tokens_kernel(const int64_t* __restrict__ tok, int rows, int S, int32_t* __restrict__ start,
+                                    int32_t* __restrict__ len) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int64_t* t = tok + (long long)row * S;
+    int first = S, last = -1;
+    for (int i = lane; i < S; i += 32)
+        if (t[i] != 0) { first = min(first, i); last = max(last, i); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    }
+    int eos = S;
+    for (int i = first + lane; i <= last; i += 32)
+        if (t[i] == 1) eos = min(eos, i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) eos = min(eos, __shfl_xor_sync(0xffffffffu, eos, o));
+    if (lane == 0) {
+        if (last < 0) { start[row] = 0; len[row] = 0; }
+        else { start[row] = first; len[row] = (eos <= last ? eos : last + 1) - first; }
+    }
+}
+
 __global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];
@@ -245,6 +271,13 @@ extern "C" int fn_transpose_f32(const float* src, long long ld_src, float* dst, 
     FN_REQUIRE(src && dst && rows > 0 && cols > 0, "fn_transpose_f32: bad args");
     dim3 grid(fn_cdiv(cols, 32), fn_cdiv(rows, 32)), block(32, 8);
     transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, rows, cols, accumulate);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+
+extern "C" int fn_clean_tokens(const int64_t* tokens, int rows, int steps, int32_t* start, int32_t* len, void* stream) {
+    FN_REQUIRE(tokens && start && len && rows > 0 && steps > 0, "fn_clean_tokens: bad args");
+    clean_tokens_kernel<<<fn_cdiv((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(tokens, rows, steps, start, len);
     FN_LAUNCH_CHECK();
     return FN_OK;
 }
