@@ -360,7 +360,7 @@ def cpu_reference(workload, steps, warmup, sample_batch=None):
     variant, B, T, H, Z, K, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = sample_batch or {"c1": 4, "c2": 16, "c2_bf16": 16, "c3": 16, "c3_f32": 16}[workload]
+    Bs = sample_batch or {"c1": 4, "c2": 8, "c2_bf16": 8, "c3": 4, "c3_f32": 4}[workload]      # the batch at which the CPU port is fastest per sequence
     w = fo.init_weights(H, Z, variant, max(K, 1), seed=0)
     st = fo.AdamState(w)
     batch = fo.synth_batch(Bs, T, seed=0)

@@ -161,6 +161,21 @@ int fn_gru_seq_fwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T
 int fn_gru_seq_bwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
                         size_t barrier_ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Greedy decode of the global decoder as ONE persistent kernel (eval-mode global_decoder, gmm_model.py:119-149
+ * with _sampling :73-80; drivers test_class.py:233-254, arousal_transfer.ipynb cells 15/17): per step cell 1
+ * (token gather + z projection) -> cell 2 -> vocabulary projection -> first arg-max -> next token, all `steps` on
+ * the device.  bf16 weights: w_hh1 / w_ih2 / w_hh2 [3H][H], w_out [V][H], emb1 [V][3H] = W_ih1[:, :V]^T;
+ * proj1 fp32 [B][3H] = z W_ih1[:, V:]^T + b_ih1.  hs1 / hs2: bf16 [steps+1][B][H] state slabs (hs1 slab 0 = the
+ * initial state linear_init_global(z), caller-filled; slab s+1 = state after step s); gi2: bf16 [steps][B][3H]
+ * scratch.  tokens: int32 [steps][B].  logits_out: fp32 [steps][B][V] (pre-softmax) or NULL.  B <= 256.
+ * ---------------------------------------------------------------------------------------- */
+size_t fn_decode_greedy_ws_bytes(int B, int steps, int H, int V);
+int fn_decode_greedy_bf16(const void* w_hh1, const float* b_hh1, const void* emb1, const float* proj1, const void* w_ih2,
+                          const float* b_ih2, const void* w_hh2, const float* b_hh2, const void* w_out, const float* b_out,
+                          void* hs1, void* hs2, void* gi2, int B, int steps, int H, int V, int start_token,
+                          int32_t* tokens, float* logits_out, void* workspace, size_t ws_bytes, void* stream);
+
 /* Profiling aid: CTA 0 of the following fn_gru_seq_*_bf16 launches writes clock64 stamps of its pipeline
  * events into `device_buffer` ((T+1)*2*16 int64); NULL switches it off. */
 int fn_gru_debug_timeline(void* device_buffer);

@@ -58,6 +58,8 @@ _SIGNATURES = {
     "fn_gru_seq_fwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_bwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
     "fn_gru_debug_timeline": (I, [V]),
+    "fn_decode_greedy_ws_bytes": (SZ, [I, I, I, I]),
+    "fn_decode_greedy_bf16": (I, [V, V, V, V, V, V, V, V, V, V, V, V, V, I, I, I, I, I, V, V, V, SZ, V]),
     "fn_cast_bf16": (I, [V, LL, LL, V, LL, LL, LL, V]),
     "fn_ids_to_onehot_bf16": (I, [V, LL, I, LL, V, V]),
     "fn_time_sum_bf16": (I, [V, I, I, I, V, V, V]),
@@ -97,7 +99,7 @@ _SIGNATURES = {
     "fn_grad_norm": (I, [V, LL, V, V, SZ, V]),
     "fn_clip_adam": (I, [V, V, V, V, LL, V, F, F, F, F, F, I, V]),
 }
-_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes",
+_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
               "fn_col_sum_scratch_bytes", "fn_reduce_scratch_bytes"}
 
 
