@@ -4,9 +4,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include "fn_tc.cuh"
+#include <mutex>
 void fn_set_error(const char*, ...) {}
 int fn_num_sms() { return 148; }
 int fn_max_smem_optin() { return 232448; }
+fn_PFN_encodeTiled fn_get_encode_tiled() { void* p = nullptr; cudaDriverEntryPointQueryResult q; cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q); return (fn_PFN_encodeTiled)p; }
+int fn_make_tmap_bf16_2d(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long ld, unsigned box_rows, unsigned box_cols) {
+    cuuint64_t dims[2] = {cols, rows}; cuuint64_t strides[1] = {ld * 2}; cuuint32_t box[2] = {box_cols, box_rows}; cuuint32_t estr[2] = {1, 1};
+    return (int)fn_get_encode_tiled()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); }
 
 template <int CONVERGED>
 __global__ void __launch_bounds__(128, 1) k_mma(int N, int n_mma, int reps, long long* out, int a_from_tmem) {
@@ -149,7 +154,71 @@ __global__ void __launch_bounds__(128, 1) k_commit(int n, int mmas, int every, i
     if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, 512); }
 }
 
+// L2 -> shared-memory ingest rate per SM: TMA (16 KB swizzled boxes, `depth` in flight) and/or cp.async from 8 warps
+__global__ void __launch_bounds__(320, 1) k_ingest(const __grid_constant__ CUtensorMap tm, const uint4* src, int rows_total, int n_boxes,
+                                                   int depth, int use_tma, int use_cpasync, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) tc::mbar_init(&full[i], 1); tc::fence_barrier_init(); }
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp == 0 && use_tma) {
+        if (lane == 0) {
+            // keep `depth` boxes in flight: issue box i after box i-depth has landed
+            for (int i = 0; i < n_boxes + depth; ++i) {
+                const int st = i % depth;
+                if (i >= depth) tc::mbar_wait(&full[st], ((i / depth) - 1) & 1);
+                if (i < n_boxes) {
+                    tc::mbar_arrive_expect_tx(&full[st], 16384);
+                    const int row = ((blockIdx.x * 7 + i) * 128) % (rows_total - 128);
+                    tc::tma_load_2d(smem + st * 16384, &tm, &full[st], (i % 16) * 64, row);
+                }
+            }
+        }
+    } else if (warp >= 2 && use_cpasync) {
+        // 8 warps, each thread 16 B per op; 16 KB "boxes" = 128 rows x 128 B: one warp op covers 4 rows
+        const int w = warp - 2;
+        uint8_t* dst = smem + 8 * 16384 + w * 8192;
+        for (int i = 0; i < n_boxes; ++i) {
+            const int row = ((blockIdx.x * 7 + i) * 128) % (rows_total - 128);
+            const uint4* base = src + ((long long)(row + w * 16) * 1024 + (i % 16) * 64) * 2 / 16;   // 16 rows per warp per box
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int rr = r * 4 + (lane >> 3);
+                fn_cp_async16(dst + ((i & 1) * 4096) + rr * 128 + (lane & 7) * 16, base + (long long)rr * 128 + (lane & 7));
+            }
+            fn_cp_async_commit();
+            fn_cp_async_wait<4>();
+        }
+        fn_cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
+}
+
 int main() {
+    {
+        long long* o; cudaMallocManaged(&o, 64);
+        const int rows_total = 8192;      // 8192 x 1024 bf16 = 16 MB: L2 resident
+        __nv_bfloat16* buf; cudaMalloc(&buf, (size_t)rows_total * 1024 * 2); cudaMemset(buf, 0, (size_t)rows_total * 1024 * 2);
+        CUtensorMap tm;
+        fn_make_tmap_bf16_2d(&tm, buf, rows_total, 1024, 1024, 128, 64);
+        const int smem = 8 * 16384 + 8 * 8192 + 1024;
+        cudaFuncSetAttribute(k_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int n_boxes = 2000;
+        for (int grid : {1, 32, 128, 148})
+            for (int mode : {1, 2, 3})
+                for (int depth : {2, 4, 8}) {
+                    if (mode == 2 && depth != 8) continue;
+                    k_ingest<<<grid, 320, smem>>>(tm, (const uint4*)buf, rows_total, n_boxes, depth, mode & 1, (mode >> 1) & 1, o);
+                    cudaDeviceSynchronize();
+                    const double bytes = (double)n_boxes * 16384 * ((mode & 1) + ((mode >> 1) & 1));
+                    printf("ingest: grid %3d  %s depth %2d: %.1f B/clk per SM  (%s)\n", grid, mode == 1 ? "TMA only     " : mode == 2 ? "cp.async only" : "TMA+cp.async ",
+                           depth, bytes / (double)o[0], cudaGetErrorString(cudaGetLastError()));
+                }
+    }
     {
         long long* o; cudaMallocManaged(&o, 64);
         cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
