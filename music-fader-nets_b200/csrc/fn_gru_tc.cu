@@ -39,12 +39,24 @@ struct TcChain {
     int reverse, dhs_f32;
 };
 
+// Warp roles (15 warps): warp 0 = state loader 0 (+ resident weights), warp 1 = MMA issuer, warps 2-3 = state loaders 1-2,
+// warps 4-11 = the 8 gate-epilogue warps, warp 12 = state loader 3, warps 13-14 = weight-tail loaders 0-1.
+// A single issuing warp sustains only ~30 B/clk of TMA ingest on B200 (tools/ubench_tc.cu: 30 / 73 / 110 / 126 B/clk
+// per SM with 1 / 2 / 3 / 4 issuing warps), so the ring stages are dealt round-robin to several loader warps.
+// (setmaxnreg re-balancing between warpgroups was tried: ptxas then spills in the 80-register control roles.)
+constexpr int kThreadsGru = 480;
+constexpr int kEpiWarp0 = 4;
+constexpr int kMaxStateLoaders = 4, kMaxTailLoaders = 2;
+__device__ __forceinline__ int state_loader_rank(int warp) { return warp == 0 ? 0 : warp == 2 ? 1 : warp == 3 ? 2 : warp == 12 ? 3 : -1; }
+__device__ __forceinline__ int tail_loader_rank(int warp) { return warp == 13 ? 0 : warp == 14 ? 1 : -1; }
+
 struct TcLaunch {
     TcChain c[kMaxChainsTc];
     unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
     long long* dbg;        // profiling aid (fn_gru_debug_timeline): [iteration][bt][16] clock64 stamps of CTA 0, or NULL
     int n_chains, nslices, B, T, H, stages, cluster;
     int kres, wst;         // resident K chunks of the weight slice; ring slots for the streamed rest (0 = all resident)
+    int ls, lw;            // issuing warps of the state stream (1..4) and of the weight-tail stream (1..2)
     int dbg_flags;         // profiling experiments only (FN_GRU_DBGFLAGS): 1 = skip the MMAs, 2 = skip the TMA loads
 };
 #define FN_STAMP(i, bt, k)                                                                       \
@@ -53,211 +65,15 @@ struct TcLaunch {
     } while (0)
 
 // =====================================================================================================
-// U = hidden units per CTA, NBT = 128-row batch tiles per chain.  BWD = false: N = 3U gate columns,
-// K = H.  BWD = true: N = U, K = 3H (A = gate gradients of the following step, pitch 4H).
+// Gate epilogue (8 warps, two warpgroups), see the kernel header below.
 // =====================================================================================================
-template <int U, int NBT, bool BWD, int KCH>
-__global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
+template <int U, int NBT, bool BWD>
+__device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& c, const Smem& sm, const uint32_t tmem_base, unsigned* gbar,
+                                              const int u0, const int warp, const int lane) {
     constexpr int N = BWD ? U : 3 * U;
-    constexpr uint32_t kAccCols = NBT * N;                     // accumulators; forward: + NBT*N projection columns
-    constexpr uint32_t kNeedCols = BWD ? kAccCols : 2 * kAccCols;
-    constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
-    static_assert(kNeedCols <= 512, "TMEM columns");
-    extern __shared__ uint8_t smem_raw[];
-    const int H = P.H, B = P.B, T = P.T, S = P.stages;
-    const int K = BWD ? 3 * H : H;
-    const int nkc = K / 64;
-    const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
-    constexpr uint32_t stage_bytes = KCH * kATile;             // one ring stage: 128 rows x (KCH * 64) K
-    // The weight slice is resident for its first `kres` K chunks; the remaining `nstream` chunks are re-streamed
-    // every (step, batch tile) through a small ring by a dedicated warp.  They do not depend on the recurrence, so
-    // that stream runs ahead of the step barrier; the K loop consumes the streamed chunks FIRST.
-    const int kres = P.kres, nstream = nkc - kres, WST = P.wst;
-    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * w_chunk_bytes, S * KCH);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
-    const TcChain& c = P.c[chain];
-    unsigned* gbar = P.bar + chain * 16;
-    const int u0 = slice * U;
-    // cluster = `csize` consecutive slices of one chain: each streams 1/csize of every state tile and multicasts it
-    const uint32_t crank = tc::cluster_ctarank(), csize = tc::cluster_nctarank();
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1);
-
-    if (warp == 0 && lane == 0) {
-        tc::prefetch_tmap(&c.tmW);
-        tc::prefetch_tmap(&c.tmA);
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], csize); }
-        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], BWD ? kEpiWarps / NBT : kEpiWarps); }
-        tc::mbar_init(sm.wbar, 1);
-        for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
-        tc::fence_barrier_init();
-    }
-    if (warp == 1) tc::tmem_alloc(sm.tmem_slot, kTmemCols);
-    if (!BWD && threadIdx.x >= 64) {
-        for (int i = threadIdx.x - 64; i < 3 * U; i += kEpiThreads) sm.bias[i] = c.b_hh[(i / U) * H + u0 + (i % U)];
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::cluster_sync();                                        // peers' barriers are initialised before any remote arrive
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *sm.tmem_slot;
-
-    // iteration i: forward step s = i (A slab = s: the state before the step);
-    // backward s = T-1-i for i = 0..T (s = -1 finishes dh0); the product of iteration i >= 1 reads slab s+1 of dg.
-    const int n_iters = BWD ? T + 1 : T;
-
-    if (warp == 0) {
-        // Control warps run CONVERGED (all 32 lanes execute the loop, one elected lane issues the async
-        // instructions): the compiler then keeps the loop state in uniform registers and issues TMA / MMA /
-        // commit without per-instruction election loops -- these single-thread loops pace the whole kernel.
-        if (tc::elect_one()) {
-            tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(kres * w_chunk_bytes));
-            for (int kc = 0; kc < kres; ++kc) {
-                if (!BWD) {
-                    for (int g = 0; g < 3; ++g)
-                        tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, sm.wbar, kc * 64, g * H + u0);
-                } else {
-                    tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes, &c.tmW, sm.wbar, kc * 64, u0);
-                }
-            }
-        }
-        __syncwarp();
-        {
-            // ---- state-slab stream.  One thread, so everything per stage is kept to a handful of instructions:
-            // raw shared addresses, incremental stage / phase / column counters, no divisions.
-            const uint32_t rows = 128u / csize;                                   // tmA's box is 64 x rows
-            const uint32_t a0 = tc::smem_u32(sm.A) + crank * rows * 128u;
-            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
-            const int row0 = (int)(crank * rows);
-            const bool mc = csize > 1, skip_tma = (P.dbg_flags & 2) != 0;
-            const int nst = nkc / KCH;                                            // stages per (step, batch tile)
-            uint32_t st = 0, ph = 1;                                              // ph: parity that means "slot free"
-            for (int i = BWD ? 1 : 0; i < n_iters; ++i) {
-                // forward: the state before step s=i;  backward (s = T-1-i): the gate gradient of step s+1
-                const int slab = BWD ? (c.reverse ? i - 1 : T - i) : (c.reverse ? T - i : i);
-                for (int bt = 0; bt < NBT; ++bt) {
-                    FN_STAMP(i, bt, 0);
-                    if (i > 0) {
-                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i) * (BWD ? kEpiWarps / NBT : kEpiWarps));
-                        FN_STAMP(i, bt, 1);
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
-                    }
-                    FN_STAMP(i, bt, 2);
-                    int col = kres * 64;                       // K order: streamed chunks [kres, nkc) first, then [0, kres)
-                    for (int j = 0; j < nst; ++j) {
-                        if (j * KCH == nstream) col = 0;
-                        const uint32_t fb = full0 + st * 8u, sa = a0 + st * stage_bytes;
-                        tc::mbar_wait_u32(empty0 + st * 8u, ph);
-                        if (tc::elect_one()) {
-                            if (skip_tma) {
-                                tc::mbar_arrive_u32(fb);
-                            } else {
-                                tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
-#pragma unroll
-                                for (int q = 0; q < KCH; ++q) {
-                                    // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
-                                    const int cq = col + q * 64;
-                                    const int cc = (BWD && cq >= 2 * H) ? cq + H : cq;
-                                    if (mc) tc::tma_load_3d_mc_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128 + row0, slab, cmask);
-                                    else tc::tma_load_3d_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128, slab);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        col += 64 * KCH;
-                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
-                    }
-                    FN_STAMP(i, bt, 3);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        {
-            const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
-            tc::mbar_wait(sm.wbar, 0);
-            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
-            const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
-            const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
-            const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
-            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
-            uint32_t ws = 0, wph = 0;
-            const uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4;   // descriptor address units (16 B)
-            const bool mc = csize > 1, skip_mma = (P.dbg_flags & 1) != 0;
-            const int nst = nkc / KCH;
-            uint32_t st = 0, ph = 0, uses = 0;
-            for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
-                for (int bt = 0; bt < NBT; ++bt) {
-                    tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
-                    tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
-                    uint64_t bd = bdesc0;
-                    for (int j = 0; j < nst; ++j) {
-                        const bool streamed = j * KCH < nstream;
-                        // streamed weight chunks of this stage: wait for them, remember their ring slots
-                        uint32_t wslot[KCH];
-                        if (streamed) {
-#pragma unroll
-                            for (int q = 0; q < KCH; ++q) {
-                                tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
-                                wslot[q] = ws;
-                                if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
-                            }
-                        }
-                        tc::mbar_wait_u32(full0 + st * 8u, ph);
-                        tc::tc_fence_after();
-                        if (j == 0) FN_STAMP(i, bt, 4);
-                        const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
-                        if (tc::elect_one()) {
-#pragma unroll
-                            for (int q = 0; q < KCH; ++q) {
-                                const uint64_t bq = streamed ? wdesc0 + (uint64_t)(wslot[q] * b_step) : bd + (uint64_t)(q * b_step);
-                                if (!skip_mma) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bq + (uint64_t)(2 * k), idesc,
-                                                     (uint32_t)((j | q | k) != 0));
-                                }
-                                if (streamed) tc::umma_commit_u32(wempty0 + wslot[q] * 8u);     // weight-ring slot reusable
-                            }
-                            if (mc) tc::umma_commit_mc_u32(empty0 + st * 8u, cmask);  // frees the slot in every CTA that fills it
-                            else tc::umma_commit_u32(empty0 + st * 8u);
-                            if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
-                        }
-                        __syncwarp();
-                        if (!streamed) bd += (uint64_t)KCH * b_step;
-                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
-                    }
-                    FN_STAMP(i, bt, 5);
-                }
-            }
-        }
-    } else if (warp == kWTailWarp) {
-        // ------------------------------- streamed part of the weight slice -----------------------------
-        if (nstream > 0) {
-            const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
-            const int n_tilesteps = (BWD ? T : T) * NBT;
-            uint32_t ws = 0, wph = 1;
-            for (int ts = 0; ts < n_tilesteps; ++ts) {
-                for (int pch = 0; pch < nstream; ++pch) {
-                    tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
-                    if (tc::elect_one()) {
-                        const uint32_t dst = wr0 + ws * (uint32_t)w_chunk_bytes, fb = wfull0 + ws * 8u;
-                        const int kcol = (kres + pch) * 64;
-                        tc::mbar_arrive_expect_tx_u32(fb, (uint32_t)w_chunk_bytes);
-                        if (!BWD) {
-#pragma unroll
-                            for (int g = 0; g < 3; ++g) tc::tma_load_2d_u32(dst + g * U * 128, &c.tmW, fb, kcol, g * H + u0);
-                        } else {
-                            tc::tma_load_2d_u32(dst, &c.tmW, fb, kcol, u0);
-                        }
-                    }
-                    __syncwarp();
-                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
-                }
-            }
-        }
-    } else {
+    constexpr uint32_t kAccCols = NBT * N;
+    const int H = P.H, B = P.B, T = P.T;
+    {
         // ------------------------------- epilogue warps --------------------------------------------
         // All 8 warps serve batch tile 0, then tile 1: warp w reads TMEM lane quarter w % 4 (32 batch rows), the
         // two warp groups split the slice's units; each thread owns (row, UT units) of every tile for the whole
@@ -265,10 +81,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
         // dense bf16 stream -- both have gate stride H, so one prefetch path serves both.
         constexpr int UT = U / 2;
         const int q = warp & 3;                  // TMEM lane quarter this warp may read (warp id % 4)
-        const int uu = ((warp - 2) >> 2) * UT;   // unit offset inside the slice
+        const int uu = ((warp - kEpiWarp0) >> 2) * UT;   // unit offset inside the slice
         const int u = u0 + uu;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const bool stamp = (threadIdx.x == 64);
+        const bool stamp = (threadIdx.x == kEpiWarp0 * 32);
 
         if constexpr (!BWD) {
             float hreg[NBT][UT];
@@ -367,7 +183,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
             constexpr int UB = (NBT == 2) ? U : U / 2;
             constexpr int CH = UB > 16 ? 16 : UB;
             constexpr int NCHK = UB / CH;
-            const int grp = (warp - 2) >> 2;
+            const int grp = (warp - kEpiWarp0) >> 2;
             const int bt = NBT == 2 ? grp : 0;
             const int uu0 = NBT == 2 ? 0 : grp * UB;
             const int b = bt * 128 + q * 32 + lane;
@@ -464,6 +280,230 @@ __global__ void __launch_bounds__(kThreadsTc, 1) gru_tc_kernel(const __grid_cons
         }
         tc::tc_fence_before();
     }
+}
+
+// =====================================================================================================
+// U = hidden units per CTA, NBT = 128-row batch tiles per chain.  BWD = false: N = 3U gate columns,
+// K = H.  BWD = true: N = U, K = 3H (A = gate gradients of the following step, pitch 4H).
+// =====================================================================================================
+template <int U, int NBT, bool BWD, int KCH>
+__global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
+    constexpr int N = BWD ? U : 3 * U;
+    constexpr uint32_t kAccCols = NBT * N;                     // accumulators; forward: + NBT*N projection columns
+    constexpr uint32_t kNeedCols = BWD ? kAccCols : 2 * kAccCols;
+    constexpr uint32_t kTmemCols = kNeedCols <= 32 ? 32 : kNeedCols <= 64 ? 64 : kNeedCols <= 128 ? 128 : kNeedCols <= 256 ? 256 : 512;
+    static_assert(kNeedCols <= 512, "TMEM columns");
+    extern __shared__ uint8_t smem_raw[];
+    const int H = P.H, B = P.B, T = P.T, S = P.stages;
+    const int K = BWD ? 3 * H : H;
+    const int nkc = K / 64;
+    const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
+    constexpr uint32_t stage_bytes = KCH * kATile;             // one ring stage: 128 rows x (KCH * 64) K
+    // The weight slice is resident for its first `kres` K chunks; the remaining `nstream` chunks are re-streamed
+    // every (step, batch tile) through a small ring by a dedicated warp.  They do not depend on the recurrence, so
+    // that stream runs ahead of the step barrier; the K loop consumes the streamed chunks FIRST.
+    const int kres = P.kres, nstream = nkc - kres, WST = P.wst;
+    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * w_chunk_bytes, S * KCH);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
+    const TcChain& c = P.c[chain];
+    unsigned* gbar = P.bar + chain * 16;
+    const int u0 = slice * U;
+    // cluster = `csize` consecutive slices of one chain: each streams 1/csize of every state tile and multicasts it
+    const uint32_t crank = tc::cluster_ctarank(), csize = tc::cluster_nctarank();
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1);
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&c.tmW);
+        tc::prefetch_tmap(&c.tmA);
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], csize); }
+        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], BWD ? kEpiWarps / NBT : kEpiWarps); }
+        tc::mbar_init(sm.wbar, 1);
+        for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(sm.tmem_slot, kTmemCols);
+    if (!BWD && warp >= kEpiWarp0 && warp < kEpiWarp0 + (int)kEpiWarps) {
+        for (int i = threadIdx.x - kEpiWarp0 * 32; i < 3 * U; i += kEpiThreads) sm.bias[i] = c.b_hh[(i / U) * H + u0 + (i % U)];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();                                        // peers' barriers are initialised before any remote arrive
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+    const int lrank = state_loader_rank(warp), trank = tail_loader_rank(warp);
+
+    // iteration i: forward step s = i (A slab = s: the state before the step);
+    // backward s = T-1-i for i = 0..T (s = -1 finishes dh0); the product of iteration i >= 1 reads slab s+1 of dg.
+    const int n_iters = BWD ? T + 1 : T;
+
+    auto state_loader_role = [&]() {
+        // Control warps run CONVERGED (all 32 lanes execute the loop, one elected lane issues the async
+        // instructions): the compiler then keeps the loop state in uniform registers and issues TMA / MMA /
+        // commit without per-instruction election loops -- these single-thread loops pace the whole kernel.
+        if (warp == 0 && tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(kres * w_chunk_bytes));
+            for (int kc = 0; kc < kres; ++kc) {
+                if (!BWD) {
+                    for (int g = 0; g < 3; ++g)
+                        tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, sm.wbar, kc * 64, g * H + u0);
+                } else {
+                    tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes, &c.tmW, sm.wbar, kc * 64, u0);
+                }
+            }
+        }
+        __syncwarp();
+        {
+            // ---- state-slab stream.  One thread, so everything per stage is kept to a handful of instructions:
+            // raw shared addresses, incremental stage / phase / column counters, no divisions.
+            const uint32_t rows = 128u / csize;                                   // tmA's box is 64 x rows
+            const uint32_t a0 = tc::smem_u32(sm.A) + crank * rows * 128u;
+            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
+            const int row0 = (int)(crank * rows);
+            const bool mc = csize > 1, skip_tma = (P.dbg_flags & 2) != 0;
+            const int nst = nkc / KCH;                                            // stages per (step, batch tile)
+            uint32_t st = 0, ph = 1;                                              // ph: parity that means "slot free"
+            int turn = 0;                                                         // stages are dealt round-robin to the loaders
+            const int LS = P.ls;
+            for (int i = BWD ? 1 : 0; i < n_iters; ++i) {
+                // forward: the state before step s=i;  backward (s = T-1-i): the gate gradient of step s+1
+                const int slab = BWD ? (c.reverse ? i - 1 : T - i) : (c.reverse ? T - i : i);
+                for (int bt = 0; bt < NBT; ++bt) {
+                    if (lrank == 0) FN_STAMP(i, bt, 0);
+                    if (i > 0) {
+                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i) * (BWD ? kEpiWarps / NBT : kEpiWarps));
+                        if (lrank == 0) FN_STAMP(i, bt, 1);
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                    }
+                    if (lrank == 0) FN_STAMP(i, bt, 2);
+                    int col = kres * 64;                       // K order: streamed chunks [kres, nkc) first, then [0, kres)
+                    for (int j = 0; j < nst; ++j) {
+                        if (j * KCH == nstream) col = 0;
+                        const uint32_t fb = full0 + st * 8u, sa = a0 + st * stage_bytes;
+                        const bool mine = (turn == lrank);
+                        if (mine) tc::mbar_wait_u32(empty0 + st * 8u, ph);
+                        if (mine && tc::elect_one()) {
+                            if (skip_tma) {
+                                tc::mbar_arrive_u32(fb);
+                            } else {
+                                tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
+#pragma unroll
+                                for (int q = 0; q < KCH; ++q) {
+                                    // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
+                                    const int cq = col + q * 64;
+                                    const int cc = (BWD && cq >= 2 * H) ? cq + H : cq;
+                                    if (mc) tc::tma_load_3d_mc_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128 + row0, slab, cmask);
+                                    else tc::tma_load_3d_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128, slab);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        col += 64 * KCH;
+                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                        if (++turn == LS) turn = 0;
+                    }
+                    if (lrank == 0) FN_STAMP(i, bt, 3);
+                }
+            }
+        }
+    };
+    auto mma_role = [&]() {
+        {
+            const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+            tc::mbar_wait(sm.wbar, 0);
+            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
+            const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
+            const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
+            const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
+            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+            uint32_t ws = 0, wph = 0;
+            const uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4;   // descriptor address units (16 B)
+            const bool mc = csize > 1, skip_mma = (P.dbg_flags & 1) != 0;
+            const int nst = nkc / KCH;
+            uint32_t st = 0, ph = 0, uses = 0;
+            for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
+                for (int bt = 0; bt < NBT; ++bt) {
+                    tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
+                    uint64_t bd = bdesc0;
+                    for (int j = 0; j < nst; ++j) {
+                        const bool streamed = j * KCH < nstream;
+                        // streamed weight chunks of this stage: wait for them, remember their ring slots
+                        uint32_t wslot[KCH];
+                        if (streamed) {
+#pragma unroll
+                            for (int q = 0; q < KCH; ++q) {
+                                tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
+                                wslot[q] = ws;
+                                if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                            }
+                        }
+                        tc::mbar_wait_u32(full0 + st * 8u, ph);
+                        tc::tc_fence_after();
+                        if (j == 0) FN_STAMP(i, bt, 4);
+                        const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
+                        if (tc::elect_one()) {
+#pragma unroll
+                            for (int q = 0; q < KCH; ++q) {
+                                const uint64_t bq = streamed ? wdesc0 + (uint64_t)(wslot[q] * b_step) : bd + (uint64_t)(q * b_step);
+                                if (!skip_mma) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bq + (uint64_t)(2 * k), idesc,
+                                                     (uint32_t)((j | q | k) != 0));
+                                }
+                                if (streamed) tc::umma_commit_u32(wempty0 + wslot[q] * 8u);     // weight-ring slot reusable
+                            }
+                            if (mc) tc::umma_commit_mc_u32(empty0 + st * 8u, cmask);  // frees the slot in every CTA that fills it
+                            else tc::umma_commit_u32(empty0 + st * 8u);
+                            if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
+                        }
+                        __syncwarp();
+                        if (!streamed) bd += (uint64_t)KCH * b_step;
+                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                    }
+                    FN_STAMP(i, bt, 5);
+                }
+            }
+        }
+    };
+    auto tail_loader_role = [&]() {
+        // ------------------------------- streamed part of the weight slice -----------------------------
+        if (nstream > 0) {
+            int turn = 0;
+            const int LW = P.lw;
+            const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+            const int n_tilesteps = (BWD ? T : T) * NBT;
+            uint32_t ws = 0, wph = 1;
+            for (int ts = 0; ts < n_tilesteps; ++ts) {
+                for (int pch = 0; pch < nstream; ++pch) {
+                    const bool mine = (turn == trank);
+                    if (++turn == LW) turn = 0;
+                    if (mine) tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
+                    if (mine && tc::elect_one()) {
+                        const uint32_t dst = wr0 + ws * (uint32_t)w_chunk_bytes, fb = wfull0 + ws * 8u;
+                        const int kcol = (kres + pch) * 64;
+                        tc::mbar_arrive_expect_tx_u32(fb, (uint32_t)w_chunk_bytes);
+                        if (!BWD) {
+#pragma unroll
+                            for (int g = 0; g < 3; ++g) tc::tma_load_2d_u32(dst + g * U * 128, &c.tmW, fb, kcol, g * H + u0);
+                        } else {
+                            tc::tma_load_2d_u32(dst, &c.tmW, fb, kcol, u0);
+                        }
+                    }
+                    __syncwarp();
+                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                }
+            }
+        }
+    };
+
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + (int)kEpiWarps) epilogue_role<U, NBT, BWD>(P, c, sm, tmem_base, gbar, u0, warp, lane);
+    else if (warp == 1) mma_role();
+    else if (lrank >= 0 && lrank < P.ls) state_loader_role();
+    else if (trank >= 0 && trank < P.lw) tail_loader_role();
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
@@ -496,7 +536,7 @@ int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(P.n_chains * P.nslices);
-    cfg.blockDim = dim3(kThreadsTc);
+    cfg.blockDim = dim3(kThreadsGru);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];
@@ -587,6 +627,15 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         const TcPlan pl = tc_plan(U, H, bwd);
         const int kch = pl.kch;
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
+        // Issuing warps per stream.  A ring slot must always be filled by the SAME loader (the "slot free" parity wait
+        // is only safe against the loader's own previous fill of that slot), so the count has to divide the slot count.
+        // Measured on config 3: 1..3 state loaders and 1..2 tail loaders give the same step period (the recurrence is
+        // bound by its synchronisation chain, not by TMA issue), hence the default of one each.
+        static const int ls_env = env_int("FN_GRU_LS", 1), lw_env = env_int("FN_GRU_LW", 1);
+        P.ls = ls_env < 1 ? 1 : ls_env > kMaxStateLoaders ? kMaxStateLoaders : ls_env;
+        P.lw = lw_env < 1 ? 1 : lw_env > kMaxTailLoaders ? kMaxTailLoaders : lw_env;
+        while (P.stages % P.ls) --P.ls;
+        while (P.wst > 0 && P.wst % P.lw) --P.lw;
         P.dbg = g_dbg;
         static const int dbg_flags = getenv("FN_GRU_DBGFLAGS") ? atoi(getenv("FN_GRU_DBGFLAGS")) : 0;
         P.dbg_flags = dbg_flags;

@@ -2,6 +2,7 @@
 // constants, TMEM / vector load-store helpers, the release/acquire publish, the shared-memory carve-up and the
 // host-side shared-memory plan.  Everything lives in an anonymous namespace of the including translation unit.
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -12,7 +13,7 @@ namespace {
 constexpr int kMaxChainsTc = 4;
 constexpr int kThreadsTc = 352;           // 2 control warps + 8 epilogue warps + 1 weight-tail producer warp
 constexpr int kWTailWarp = 10;
-constexpr int kMaxWst = 8;                // slots of the streamed-weight ring
+constexpr int kMaxWst = 32;               // slots of the streamed-weight ring
 constexpr int kEpiThreads = 256;
 constexpr int kATile = 128 * 64 * 2;      // 16 KB: 128 batch rows x 64 K (bf16), one 128B-swizzle atom wide
 constexpr int kMaxStages = 8;
@@ -156,7 +157,7 @@ __device__ __forceinline__ Smem carve(uint8_t* smem_raw, int w_res_bytes, int w_
 }
 
 // ---- host: shared-memory plan ---------------------------------------------------------------------------
-constexpr size_t kSmemTail = 1024 /*align*/ + 512 /*barriers*/ + 3 * 64 * 4 /*bias*/;
+constexpr size_t kSmemTail = 1024 /*align*/ + 1024 /*barriers*/ + 3 * 64 * 4 /*bias*/;
 
 // Shared-memory plan of one kernel instance: how many K chunks of the weight slice stay resident, the ring
 // that re-streams the others, and the state-slab ring.
@@ -175,8 +176,10 @@ TcPlan tc_plan(int U, int H, bool bwd) {
     const int N = bwd ? U : 3 * U, nkc = (bwd ? 3 * H : H) / 64;
     const long long w_chunk = (long long)N * 128;
     const long long budget = (long long)fn_max_smem_optin() - (long long)kSmemTail;
-    static const int min_ring_kb = env_int("FN_GRU_RING_KB", 96);      // state ring when the weights do not all fit
-    static const int wring_kb = env_int("FN_GRU_WRING_KB", 32);
+    static const int ring_kb_f = env_int("FN_GRU_RING_KB", 96);        // state ring when the weights do not all fit
+    static const int wring_kb_f = env_int("FN_GRU_WRING_KB", 32);
+    static const int ring_kb_b = env_int("FN_GRU_RING_KB_BWD", ring_kb_f), wring_kb_b = env_int("FN_GRU_WRING_KB_BWD", wring_kb_f);
+    const int min_ring_kb = bwd ? ring_kb_b : ring_kb_f, wring_kb = bwd ? wring_kb_b : wring_kb_f;
     pl.kch = (nkc % 2 == 0) ? 2 : 1;
     long long room = budget - nkc * w_chunk;                            // ring space with a fully resident slice
     if (room >= 6LL * kATile) {
@@ -200,6 +203,8 @@ TcPlan tc_plan(int U, int H, bool bwd) {
     pl.stages = (int)(tiles / pl.kch);
     if (pl.stages > kMaxStages) pl.stages = kMaxStages;
     pl.ok = pl.stages >= 2;
+    static const int verbose = env_int("FN_GRU_VERBOSE", 0);
+    if (verbose) fprintf(stderr, "tc_plan U=%d H=%d bwd=%d: kch=%d stages=%d kres=%d/%d wst=%d\n", U, H, (int)bwd, pl.kch, pl.stages, pl.kres, nkc, pl.wst);
     pl.smem = (size_t)(pl.kres * w_chunk + pl.wst * w_chunk + (long long)pl.stages * pl.kch * kATile) + kSmemTail;
     return pl;
 }

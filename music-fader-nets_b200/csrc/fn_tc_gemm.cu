@@ -4,6 +4,8 @@
 // One 128x128 output tile per CTA; 3 smem stages (96 KB) so two CTAs share an SM and one tile's epilogue
 // overlaps the other's main loop.  Both operands may be K-major or MN-major (transposed in memory), which
 // covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without materialising any transpose.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "fn_tc.cuh"
@@ -25,6 +27,7 @@ struct GemmParams {
     int M, N, K;
     int a_mn, b_mn, c_bf16, accumulate;
     int splits, kb_per_split;      // split-K: grid.z CTAs per output tile, each owning kb_per_split K blocks
+    int issue_lanes;               // lanes of the producer warp that issue TMA boxes (1, 2 or 4)
     float* partial;                // [splits][M][N] fp32 partial products (splits > 1), reduced by splitk_reduce_kernel
 };
 
@@ -62,24 +65,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t st = 0, ph = 1;
         for (int kb = 0; kb < nkb; ++kb) {
             tc::mbar_wait_u32(empty0 + st * 8u, ph);                   // slot free (passes immediately on first lap)
-            if (tc::elect_one()) {
-                uint8_t* sa = smem + st * kStageBytes;
-                uint8_t* sb = sa + kTileBytes;
-                uint64_t* fb = &full[st];
-                tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, kStageBytes);
-                const int k0 = (kb_first + kb) * BK;
-                if (!p.a_mn) {
-                    tc::tma_load_2d(sa, &tmA, fb, k0, m0);                             // box 64(K) x 128(M)
-                } else {
-                    tc::tma_load_2d(sa, &tmA, fb, m0, k0);                             // box 64(M) x 64(K)
-                    tc::tma_load_2d(sa + kTileBytes / 2, &tmA, fb, m0 + 64, k0);
-                }
-                if (!p.b_mn) {
-                    tc::tma_load_2d(sb, &tmB, fb, k0, n0);
-                } else {
-                    tc::tma_load_2d(sb, &tmB, fb, n0, k0);
-                    tc::tma_load_2d(sb + kTileBytes / 2, &tmB, fb, n0 + 64, k0);
-                }
+            // A stage is 4 boxes of 64 rows x 64 columns (8 KB): lanes 0..3 issue one each.  One issuing thread
+            // sustains only one TMA op per ~450 cycles on B200 (tools/ubench_tc.cu), whatever the box size; several
+            // lanes of one converged instruction scale almost linearly (8 boxes of 32 rows measured slower than 4 of 64).
+            if (lane == 0) tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, kStageBytes);
+            for (int op = lane; op < 4; op += p.issue_lanes) {
+                if (lane >= p.issue_lanes) break;
+                const int operand = op >> 1, half = op & 1;
+                const CUtensorMap* tm = operand ? &tmB : &tmA;
+                const int mn_major = operand ? p.b_mn : p.a_mn;
+                const int r0 = (operand ? n0 : m0) + half * 64, k0 = (kb_first + kb) * BK;
+                const uint32_t dst = s0 + st * kStageBytes + operand * kTileBytes + half * (kTileBytes / 2);
+                // K-major: box 64(K) x 64(M|N rows), the second half of the tile starts 64 rows * 128 B further on;
+                // MN-major: box 64(M|N) x 64(K), the second 64-wide M|N block starts kTileBytes / 2 further on
+                tc::tma_load_2d_u32(dst, tm, full0 + st * 8u, mn_major ? r0 : k0, mn_major ? k0 : r0);
             }
             __syncwarp();
             if (++st == kStages) { st = 0; ph ^= 1u; }
@@ -296,13 +295,14 @@ extern "C" int fn_tc_gemm_bf16_splitk(const void* A, long long lda, int a_mn_maj
     CUtensorMap tmA, tmB;
     int rc;
     // K-major operand: memory [rows = M|N][cols = K];  MN-major operand: memory [rows = K][cols = M|N]
-    rc = a_mn_major ? fn_make_tmap_bf16_2d(&tmA, A, K, M, lda, 64, 64) : fn_make_tmap_bf16_2d(&tmA, A, M, K, lda, 128, 64);
+    rc = a_mn_major ? fn_make_tmap_bf16_2d(&tmA, A, K, M, lda, 64, 64) : fn_make_tmap_bf16_2d(&tmA, A, M, K, lda, 64, 64);
     if (rc) return rc;
-    rc = b_mn_major ? fn_make_tmap_bf16_2d(&tmB, B, K, N, ldb, 64, 64) : fn_make_tmap_bf16_2d(&tmB, B, N, K, ldb, 128, 64);
+    rc = b_mn_major ? fn_make_tmap_bf16_2d(&tmB, B, K, N, ldb, 64, 64) : fn_make_tmap_bf16_2d(&tmB, B, N, K, ldb, 64, 64);
     if (rc) return rc;
+    static const int issue_lanes = getenv("FN_GEMM_LANES") ? atoi(getenv("FN_GEMM_LANES")) : 4;
     const int kb_per_split = splits > 1 ? (nkb_total + splits - 1) / splits : (nkb_total > 0 ? nkb_total : 1);
     GemmParams p{C, bias, ldc, M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, c_bf16 ? 1 : 0, accumulate ? 1 : 0,
-                 splits, kb_per_split, reinterpret_cast<float*>(workspace)};
+                 splits, kb_per_split, issue_lanes, reinterpret_cast<float*>(workspace)};
     static bool attr_done = false;
     if (!attr_done) {
         FN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

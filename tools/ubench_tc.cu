@@ -198,7 +198,93 @@ __global__ void __launch_bounds__(320, 1) k_ingest(const __grid_constant__ CUten
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
 }
 
+// 1-D bulk copies (cp.async.bulk, no tensor map): `bytes` contiguous per op, `depth` in flight
+__global__ void __launch_bounds__(128, 1) k_bulk(const uint8_t* src, long long src_bytes, int n_ops, int bytes, int depth, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[8];
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) tc::mbar_init(&full[i], 1); tc::fence_barrier_init(); }
+    __syncthreads();
+    const long long t0 = clock64();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n_ops + depth; ++i) {
+            const int st = i % depth;
+            if (i >= depth) tc::mbar_wait(&full[st], ((i / depth) - 1) & 1);
+            if (i < n_ops) {
+                tc::mbar_arrive_expect_tx(&full[st], bytes);
+                const long long off = (((long long)blockIdx.x * 7 + i) * bytes) % (src_bytes - bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(tc::smem_u32(smem + st * 16384)), "l"(src + (off & ~15LL)), "r"(bytes), "r"(tc::smem_u32(&full[st])) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
+}
+
+// tensor-TMA ingest with several ISSUING warps (or, lanes_mode, several lanes of warp 0), each its own 2-deep ring of boxes
+__global__ void __launch_bounds__(256, 1) k_ingest_mw(const __grid_constant__ CUtensorMap tm, int rows_total, int n_boxes, int nprod, int box_rows,
+                                                      int lanes_mode, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[8][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) { tc::mbar_init(&full[i][0], 1); tc::mbar_init(&full[i][1], 1); } tc::fence_barrier_init(); }
+    __syncthreads();
+    const long long t0 = clock64();
+    const int me = lanes_mode ? lane : warp;
+    const bool active = lanes_mode ? (warp == 0 && lane < nprod) : (warp < nprod && lane == 0);
+    const int box_bytes = box_rows * 128;
+    if (active) {
+        for (int i = 0; i < n_boxes + 2; ++i) {
+            const int st = i & 1;
+            if (i >= 2) tc::mbar_wait(&full[me][st], ((i >> 1) - 1) & 1);
+            if (i < n_boxes) {
+                tc::mbar_arrive_expect_tx(&full[me][st], box_bytes);
+                const int row = ((blockIdx.x * 7 + i * nprod + me) * box_rows) % (rows_total - box_rows);
+                tc::tma_load_2d(smem + (me * 2 + st) * box_bytes, &tm, &full[me][st], (i % 16) * 64, row);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
+}
+
 int main() {
+    {
+        long long* o; cudaMallocManaged(&o, 64);
+        const int rows_total = 8192;
+        __nv_bfloat16* buf; cudaMalloc(&buf, (size_t)rows_total * 1024 * 2); cudaMemset(buf, 0, (size_t)rows_total * 1024 * 2);
+        const int smem = 12 * 16384 + 1024;
+        cudaFuncSetAttribute(k_ingest_mw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int box_rows : {32, 128, 256}) {
+            CUtensorMap tm;
+            fn_make_tmap_bf16_2d(&tm, buf, rows_total, 1024, 1024, box_rows, 64);
+            for (int lanes_mode : {0, 1})
+                for (int grid : {1, 128})
+                    for (int np : {1, 2, 3, 4, 6}) {
+                        if (np * 2 * box_rows * 128 > 12 * 16384) continue;
+                        k_ingest_mw<<<grid, 256, smem>>>(tm, rows_total, 1000, np, box_rows, lanes_mode, o); cudaDeviceSynchronize();
+                        printf("tma-multi: box %3d rows, grid %3d issuing %s %d: %.1f B/clk per SM (%.0f clk per op per issuer) (%s)\n", box_rows, grid,
+                               lanes_mode ? "lanes" : "warps", np, 1000.0 * np * box_rows * 128 / (double)o[0], (double)o[0] / 1000.0,
+                               cudaGetErrorString(cudaGetLastError()));
+                    }
+        }
+    }
+    {
+        long long* o; cudaMallocManaged(&o, 64);
+        const long long nb = 16ll << 20;
+        uint8_t* buf; cudaMalloc(&buf, nb); cudaMemset(buf, 0, nb);
+        const int smem = 8 * 16384 + 1024;
+        cudaFuncSetAttribute(k_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int grid : {1, 128})
+            for (int bytes : {2048, 8192, 16384})
+                for (int depth : {2, 8}) {
+                    k_bulk<<<grid, 128, smem>>>(buf, nb, 2000, bytes, depth, o); cudaDeviceSynchronize();
+                    printf("bulk1d: grid %3d %5d B per op depth %d: %.1f B/clk per SM (%s)\n", grid, bytes, depth, 2000.0 * bytes / (double)o[0],
+                           cudaGetErrorString(cudaGetLastError()));
+                }
+    }
     {
         long long* o; cudaMallocManaged(&o, 64);
         const int rows_total = 8192;      // 8192 x 1024 bf16 = 16 MB: L2 resident
