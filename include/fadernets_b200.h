@@ -33,7 +33,7 @@ extern "C" {
 #define FN_ERR_CUDA (-2)     /* a CUDA runtime call failed        */
 #define FN_ERR_UNSUPPORTED (-3)
 
-#define FN_ABI_VERSION 1
+#define FN_ABI_VERSION 2
 
 const char* fn_last_error(void);
 int fn_abi_version(void);
@@ -270,6 +270,10 @@ int fn_sum_f32(const float* x, long long n, float scale, float* out, void* scrat
 /* ------------------------------------------------------------------------------------------
  * Latent block.
  * ---------------------------------------------------------------------------------------- */
+/* Caller-owned scratch of the reductions below (two fixed-order stages: per-CTA partials, then one sum), for a
+ * latent block of B rows x Z dims and K mixture components.  The reductions stream at HBM bandwidth for large B
+ * and are run-to-run deterministic.  scratch == NULL selects the single-CTA kernels (small B only). */
+size_t fn_latent_scratch_bytes(int B, int Z, int K);
 /* scale = exp(pre)  (var_r(x).exp_(), gmm_model.py:86,91) and z = mu + scale*eps (repar, :229-235) */
 int fn_reparam_fwd(const float* mu, const float* pre_scale, const float* eps, long long n, float* scale, float* z,
                    void* stream);
@@ -283,7 +287,7 @@ int fn_qy_x_fwd(const float* z, const float* mu_lookup, const float* logvar_look
 /* given dlogLogit, dqy: dz (B,Z), dmu_lookup (K,Z) (+= if accumulate) */
 int fn_qy_x_bwd(const float* z, const float* mu_lookup, const float* logvar_lookup, const float* qy,
                 const float* dlogLogit, const float* dqy, int B, int Z, int K, float* dz, float* dmu_lookup,
-                void* stream);
+                void* scratch, size_t scratch_bytes, void* stream);
 /* GM-VAE KL block (trainer_gmm.py:140-194).  mode 0 = unsupervised, 1 = supervised (y_label).
  * out[0] = kld_lat (sum_k mean_b(mean_z KL(q||p_k) * qy[b,k]))   [sup: mean_b mean_z KL(q||p_y)]
  * out[1] = kld_cls ((mean_k(qy*log_softmax(logLogit)) - ln(1/K)).mean())  [sup: 0]
@@ -291,14 +295,15 @@ int fn_qy_x_bwd(const float* z, const float* mu_lookup, const float* logvar_look
  * p_k = Normal(mu_k, scale = exp(logvar_k))  (sic: exp(logvar) used as scale, :156-157). */
 int fn_gm_kl_fwd(const float* mu, const float* scale, const float* mu_lookup, const float* logvar_lookup,
                  const float* qy, const float* logLogit, const int64_t* y_label, int mode, int B, int Z, int K,
-                 float* out3, void* stream);
+                 float* out3, void* scratch, size_t scratch_bytes, void* stream);
 /* grads wrt (mu, scale, qy, logLogit, mu_lookup) given dout3 (device, 3 floats). */
 int fn_gm_kl_bwd(const float* mu, const float* scale, const float* mu_lookup, const float* logvar_lookup,
                  const float* qy, const float* logLogit, const int64_t* y_label, int mode, int B, int Z, int K,
                  const float* dout3, float* dmu, float* dscale, float* dqy, float* dlogLogit, float* dmu_lookup,
-                 void* stream);
+                 void* scratch, size_t scratch_bytes, void* stream);
 /* vanilla VAE: out[0] = mean_{B,Z} KL(N(mu,scale) || N(0,1))  (trainer.py:104-109) */
-int fn_std_kl_fwd(const float* mu, const float* scale, long long n, float* out, void* stream);
+int fn_std_kl_fwd(const float* mu, const float* scale, long long n, float* out, void* scratch, size_t scratch_bytes,
+                  void* stream);
 int fn_std_kl_bwd(const float* mu, const float* scale, long long n, const float* dout, float* dmu, float* dscale,
                   void* stream);
 /* Pati et al. latent regularisation (trainer_gmm.py:199-217): l = mean_{i,j}(tanh(z0_i - z0_j) -

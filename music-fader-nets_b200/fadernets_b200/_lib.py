@@ -89,17 +89,18 @@ _SIGNATURES = {
     "fn_reparam_fwd": (I, [V, V, V, LL, V, V, V]),
     "fn_reparam_bwd": (I, [V, V, V, V, V, LL, V, V, V]),
     "fn_qy_x_fwd": (I, [V, V, V, I, I, I, V, V, V, V]),
-    "fn_qy_x_bwd": (I, [V, V, V, V, V, V, I, I, I, V, V, V]),
-    "fn_gm_kl_fwd": (I, [V, V, V, V, V, V, V, I, I, I, I, V, V]),
-    "fn_gm_kl_bwd": (I, [V, V, V, V, V, V, V, I, I, I, I, V, V, V, V, V, V, V]),
-    "fn_std_kl_fwd": (I, [V, V, LL, V, V]),
+    "fn_qy_x_bwd": (I, [V, V, V, V, V, V, I, I, I, V, V, V, SZ, V]),
+    "fn_gm_kl_fwd": (I, [V, V, V, V, V, V, V, I, I, I, I, V, V, SZ, V]),
+    "fn_latent_scratch_bytes": (SZ, [I, I, I]),
+    "fn_gm_kl_bwd": (I, [V, V, V, V, V, V, V, I, I, I, I, V, V, V, V, V, V, V, SZ, V]),
+    "fn_std_kl_fwd": (I, [V, V, LL, V, V, SZ, V]),
     "fn_std_kl_bwd": (I, [V, V, LL, V, V, V, V]),
     "fn_latent_reg_fwd": (I, [V, LL, V, I, V, V, V, V]),
     "fn_latent_reg_bwd": (I, [V, V, I, I, V, V]),
     "fn_grad_norm": (I, [V, LL, V, V, SZ, V]),
     "fn_clip_adam": (I, [V, V, V, V, LL, V, F, F, F, F, F, I, V]),
 }
-_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
+_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_latent_scratch_bytes", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
               "fn_col_sum_scratch_bytes", "fn_reduce_scratch_bytes"}
 
 

@@ -431,6 +431,12 @@ class NllMeanFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # latent block
 # ------------------------------------------------------------------------------------------------
+def _latent_scratch(B, Z, K, dev):
+    """Caller-owned scratch of the two-stage latent reductions (fn_latent_scratch_bytes)."""
+    nb = int(LIB.call("fn_latent_scratch_bytes", B, Z, K))
+    return torch.empty(max(nb, 16), dtype=torch.uint8, device=dev), nb
+
+
 class LatentHeadFn(torch.autograd.Function):
     """scale = exp(pre);  z = mu + scale * eps."""
 
@@ -498,7 +504,8 @@ class QyXFn(torch.autograd.Function):
         dll = None if dll is None else _f32c(dll)
         dqy = None if dqy is None else _f32c(dqy)
         dz, dmul = torch.empty_like(z), torch.empty_like(mul)
-        LIB.call("fn_qy_x_bwd", _p(z), _p(mul), _p(lvl), _p(qy), _p(dll), _p(dqy), B, Z, K, _p(dz), _p(dmul), _st(z))
+        ws, nb = _latent_scratch(B, Z, K, z.device)
+        LIB.call("fn_qy_x_bwd", _p(z), _p(mul), _p(lvl), _p(qy), _p(dll), _p(dqy), B, Z, K, _p(dz), _p(dmul), _p(ws), nb, _st(z))
         return dz, dmul, None
 
 
@@ -513,8 +520,9 @@ class GmKlFn(torch.autograd.Function):
         if y_label is not None:
             y_label = y_label.long().contiguous()
         out = torch.empty(3, dtype=F32, device=mu.device)
+        ws, nb = _latent_scratch(B, Z, K, mu.device)
         LIB.call("fn_gm_kl_fwd", _p(mu), _p(scale), _p(mu_lookup), _p(logvar_lookup), _p(qy), _p(ll), _p(y_label),
-                 mode, B, Z, K, _p(out), _st(out))
+                 mode, B, Z, K, _p(out), _p(ws), nb, _st(out))
         ctx.save_for_backward(mu, scale, mu_lookup, logvar_lookup, qy, ll)
         ctx.y_label, ctx.mode = y_label, mode
         return out
@@ -527,8 +535,9 @@ class GmKlFn(torch.autograd.Function):
         dout = _f32c(dout)
         dmu, dsc = torch.empty_like(mu), torch.empty_like(scale)
         dqy, dll, dmul = torch.empty_like(qy), torch.empty_like(ll), torch.empty_like(mul)
+        ws, nb = _latent_scratch(B, Z, K, mu.device)
         LIB.call("fn_gm_kl_bwd", _p(mu), _p(scale), _p(mul), _p(lvl), _p(qy), _p(ll), _p(ctx.y_label), ctx.mode,
-                 B, Z, K, _p(dout), _p(dmu), _p(dsc), _p(dqy), _p(dll), _p(dmul), _st(mu))
+                 B, Z, K, _p(dout), _p(dmu), _p(dsc), _p(dqy), _p(dll), _p(dmul), _p(ws), nb, _st(mu))
         return dmu, dsc, dmul, None, dqy, dll, None, None
 
 
@@ -539,7 +548,8 @@ class StdKlFn(torch.autograd.Function):
     def forward(ctx, mu, scale):
         mu, scale = _f32c(mu), _f32c(scale)
         out = torch.empty((), dtype=F32, device=mu.device)
-        LIB.call("fn_std_kl_fwd", _p(mu), _p(scale), mu.numel(), _p(out), _st(out))
+        ws, nb = _latent_scratch(mu.shape[0], mu.shape[-1], 1, mu.device)
+        LIB.call("fn_std_kl_fwd", _p(mu), _p(scale), mu.numel(), _p(out), _p(ws), nb, _st(out))
         ctx.save_for_backward(mu, scale)
         return out
 

@@ -161,11 +161,13 @@ def test_token_plumbing(dev):
     assert ops.onehot_to_ids_tm(x).view(-1).tolist() == [5, 341, 0]
 
 
+@pytest.mark.parametrize("B,Z", [(37, 24), (300, 128), (33, 23), (70, 260), (1500, 128)])
 @pytest.mark.parametrize("K", [1, 2, 4])
-def test_latent_block(dev, K):
+def test_latent_block(dev, K, B, Z):
+    """Latent block against a torch fp64 restatement.  (B, Z) cover the streaming kernels (Z % 4 == 0: one and several
+    float4 chunks per lane, more rows than one pass of the grid) and the scalar fallback (Z = 23)."""
     from fadernets_b200.ops import ExpFn, GmKlFn, LatentHeadFn, LatentRegFn, QyXFn, StdKlFn
     from torch.distributions import Normal, kl_divergence
-    B, Z = 37, 24
     mu = rnd(B, Z, seed=1, dev=dev).requires_grad_(True)
     pre = rnd(B, Z, seed=2, dev=dev, scale=0.3).requires_grad_(True)
     eps = rnd(B, Z, seed=3, dev=dev)
@@ -203,14 +205,14 @@ def test_latent_block(dev, K):
         a = attr.numpy()
         sg = torch.sign(torch.from_numpy(np.subtract.outer(a, a)).float()).double().to(dev)
         lrr = ((torch.tanh(z_[:, 0].reshape(-1, 1) - z_[:, 0]) - sg) ** 2).mean()
-        close(z, z_, what="z"); close(ll, llr, rtol=1e-5, atol=1e-3, what="logLogit"); close(qy, qyr, what="qy")
+        close(z, z_, what="z"); close(ll, llr, rtol=1e-5, atol=1e-3, what="logLogit"); close(qy, qyr, rtol=1e-4, atol=4e-4, what="qy")   # logits of magnitude ~Z e^4: one fp32 ulp of the logit is ~5e-4
         assert torch.equal(y, qyr.max(1)[1])
         close(kl[0], lat, what=f"kld_lat mode {mode}"); close(kl[1], cls, what="kld_cls"); close(kl[2], clf, what="clf")
         close(sk, skr, what="std kl"); close(lr, lrr, what="latent reg")
         totr = 1.3 * lat + 0.7 * cls + 0.9 * clf + 0.5 * skr + 2.0 * lrr + (llr * 0.01).sum() + (qyr * qyr).sum()
         rg = torch.autograd.grad(totr, [m_, p_, l_])
         for nm, x, y_ in zip(("mu", "pre", "mu_lookup"), g, rg):
-            close(x, y_, rtol=3e-4, atol=1e-5, what=f"grad {nm} mode {mode}")
+            close(x, y_, rtol=1e-3, atol=1e-5, what=f"grad {nm} mode {mode}")   # the path's fp32 bar is 1e-3
 
 
 def test_clip_adam_matches_torch(dev):
