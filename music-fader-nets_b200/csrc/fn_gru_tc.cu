@@ -61,7 +61,7 @@ struct TcLaunch {
 };
 #define FN_STAMP(i, bt, k)                                                                       \
     do {                                                                                         \
-        if (P.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) P.dbg[((long long)(i) * kMaxNbt + (bt)) * 16 + (k)] = clock64(); \
+        if (dbg_on) P.dbg[((long long)(i) * kMaxNbt + (bt)) * 64 + (k)] = clock64(); \
     } while (0)
 
 // =====================================================================================================
@@ -73,6 +73,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
     constexpr int N = BWD ? U : 3 * U;
     constexpr uint32_t kAccCols = NBT * N;
     const int H = P.H, B = P.B, T = P.T;
+    const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     {
         // ------------------------------- epilogue warps --------------------------------------------
         // All 8 warps serve batch tile 0, then tile 1: warp w reads TMEM lane quarter w % 4 (32 batch rows), the
@@ -303,9 +304,10 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
     // every (step, batch tile) through a small ring by a dedicated warp.  They do not depend on the recurrence, so
     // that stream runs ahead of the step barrier; the K loop consumes the streamed chunks FIRST.
     const int kres = P.kres, nstream = nkc - kres, WST = P.wst;
-    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * w_chunk_bytes, S * KCH);
+    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * KCH * w_chunk_bytes, S * KCH);   // a tail slot = the KCH chunks of one stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;      // profiling stamps (fn_gru_debug_timeline)
     const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
     const TcChain& c = P.c[chain];
     unsigned* gbar = P.bar + chain * 16;
@@ -424,38 +426,39 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
             uint32_t st = 0, ph = 0, uses = 0;
             for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
                 for (int bt = 0; bt < NBT; ++bt) {
+                    FN_STAMP(i, bt, 11);
                     tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
                     tc::tc_fence_after();
+                    FN_STAMP(i, bt, 12);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
                     uint64_t bd = bdesc0;
                     for (int j = 0; j < nst; ++j) {
                         const bool streamed = j * KCH < nstream;
-                        // streamed weight chunks of this stage: wait for them, remember their ring slots
-                        uint32_t wslot[KCH];
+                        // streamed weight chunks of this stage (one tail-ring slot): wait for them
+                        uint32_t wsl = 0;
                         if (streamed) {
-#pragma unroll
-                            for (int q = 0; q < KCH; ++q) {
-                                tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
-                                wslot[q] = ws;
-                                if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
-                            }
+                            tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
+                            wsl = ws;
+                            if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
                         }
+                        if (j < 12) FN_STAMP(i, bt, 16 + 2 * j);          // weight chunks of the stage present
                         tc::mbar_wait_u32(full0 + st * 8u, ph);
                         tc::tc_fence_after();
                         if (j == 0) FN_STAMP(i, bt, 4);
+                        if (j < 12) FN_STAMP(i, bt, 17 + 2 * j);          // state chunks of the stage present
                         const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
                         if (tc::elect_one()) {
 #pragma unroll
                             for (int q = 0; q < KCH; ++q) {
-                                const uint64_t bq = streamed ? wdesc0 + (uint64_t)(wslot[q] * b_step) : bd + (uint64_t)(q * b_step);
+                                const uint64_t bq = streamed ? wdesc0 + (uint64_t)((wsl * KCH + q) * b_step) : bd + (uint64_t)(q * b_step);
                                 if (!skip_mma) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                         tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bq + (uint64_t)(2 * k), idesc,
                                                      (uint32_t)((j | q | k) != 0));
                                 }
-                                if (streamed) tc::umma_commit_u32(wempty0 + wslot[q] * 8u);     // weight-ring slot reusable
                             }
+                            if (streamed) tc::umma_commit_u32(wempty0 + wsl * 8u);              // weight-ring slot reusable
                             if (mc) tc::umma_commit_mc_u32(empty0 + st * 8u, cmask);  // frees the slot in every CTA that fills it
                             else tc::umma_commit_u32(empty0 + st * 8u);
                             if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
@@ -475,22 +478,27 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
             int turn = 0;
             const int LW = P.lw;
             const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
-            const int n_tilesteps = (BWD ? T : T) * NBT;
+            const int n_tilesteps = T * NBT, nsst = nstream / KCH;           // streamed stages per (step, batch tile)
+            const uint32_t slot_bytes = (uint32_t)(KCH * w_chunk_bytes);
             uint32_t ws = 0, wph = 1;
             for (int ts = 0; ts < n_tilesteps; ++ts) {
-                for (int pch = 0; pch < nstream; ++pch) {
+                for (int pst = 0; pst < nsst; ++pst) {
                     const bool mine = (turn == trank);
                     if (++turn == LW) turn = 0;
                     if (mine) tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
                     if (mine && tc::elect_one()) {
-                        const uint32_t dst = wr0 + ws * (uint32_t)w_chunk_bytes, fb = wfull0 + ws * 8u;
-                        const int kcol = (kres + pch) * 64;
-                        tc::mbar_arrive_expect_tx_u32(fb, (uint32_t)w_chunk_bytes);
-                        if (!BWD) {
+                        const uint32_t dst = wr0 + ws * slot_bytes, fb = wfull0 + ws * 8u;
+                        tc::mbar_arrive_expect_tx_u32(fb, slot_bytes);
 #pragma unroll
-                            for (int g = 0; g < 3; ++g) tc::tma_load_2d_u32(dst + g * U * 128, &c.tmW, fb, kcol, g * H + u0);
-                        } else {
-                            tc::tma_load_2d_u32(dst, &c.tmW, fb, kcol, u0);
+                        for (int q = 0; q < KCH; ++q) {
+                            const int kcol = (kres + pst * KCH + q) * 64;
+                            if (!BWD) {
+#pragma unroll
+                                for (int g = 0; g < 3; ++g)
+                                    tc::tma_load_2d_u32(dst + q * w_chunk_bytes + g * U * 128, &c.tmW, fb, kcol, g * H + u0);
+                            } else {
+                                tc::tma_load_2d_u32(dst + q * w_chunk_bytes, &c.tmW, fb, kcol, u0);
+                            }
                         }
                     }
                     __syncwarp();
@@ -522,7 +530,7 @@ int pick_u_tc(int n_chains, int H) {
     for (int U : {32, 16}) {
         if (force_u && U != force_u) continue;
         if (H % U) continue;
-        if (!tc_plan(U, H, false).ok || !tc_plan(U, H, true).ok) continue;
+        if (!tc_plan(U, H, false, true).ok || !tc_plan(U, H, true, true).ok) continue;
         if ((long long)n_chains * (H / U) > sms) continue;
         return U;
     }
@@ -569,7 +577,8 @@ int dispatch_tc2(int U, int nbt, const TcLaunch& P, size_t smem, cudaStream_t st
 }
 template <bool BWD>
 int dispatch_tc(int U, int nbt, int kch, const TcLaunch& P, size_t smem, cudaStream_t st) {
-    return kch == 2 ? dispatch_tc2<BWD, 2>(U, nbt, P, smem, st) : dispatch_tc2<BWD, 1>(U, nbt, P, smem, st);
+    return kch == 4 ? dispatch_tc2<BWD, 4>(U, nbt, P, smem, st)
+         : kch == 2 ? dispatch_tc2<BWD, 2>(U, nbt, P, smem, st) : dispatch_tc2<BWD, 1>(U, nbt, P, smem, st);
 }
 
 int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
@@ -624,7 +633,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
         P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H;
-        const TcPlan pl = tc_plan(U, H, bwd);
+        const TcPlan pl = tc_plan(U, H, bwd, true);
         const int kch = pl.kch;
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
         // Issuing warps per stream.  A ring slot must always be filled by the SAME loader (the "slot free" parity wait
@@ -648,7 +657,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
 
 }  // namespace
 
-// Profiling aid: when set (device buffer of >= (T+1)*2*16 int64), CTA 0 of every following launch records
+// Profiling aid: when set (device buffer of >= (T+1)*2*64 int64), CTA 0 of every following launch records
 // clock64 stamps of its pipeline events (see FN_STAMP).  NULL switches it off.  Not part of the product path.
 extern "C" int fn_gru_debug_timeline(void* device_buffer) {
     g_dbg = reinterpret_cast<long long*>(device_buffer);

@@ -117,11 +117,14 @@ __device__ __forceinline__ void stb(__nv_bfloat16* p, const float (&v)[W]) {
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// Gate non-linearities of the bf16 path: ONE SFU instruction each (tanh.approx.f32, max relative error 2^-11 --
+// a quarter of the bf16 rounding the saved gates and the MMA operand get anyway), sigmoid(x) = 0.5 tanh(0.5 x) + 0.5.
 __device__ __forceinline__ float fast_tanh(float x) {
-    // tanh(x) = 2*sigmoid(2x) - 1 ; exact to ~1e-6 relative with the SFU exp, far below bf16 resolution
-    return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f;
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 
 constexpr unsigned kEpiWarps = kEpiThreads / 32;
 // Each epilogue warp publishes its part of a finished (step, batch tile) to the other slices of the chain:
@@ -171,41 +174,60 @@ struct TcPlan {
 };
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
-TcPlan tc_plan(int U, int H, bool bwd) {
+// slot_per_stage: a weight-ring slot holds the kch chunks of one stage (fn_gru_tc.cu) instead of one chunk (fn_decode_tc.cu).
+TcPlan tc_plan_k(int U, int H, bool bwd, bool slot_per_stage, int kch_req) {
     TcPlan pl{};
     const int N = bwd ? U : 3 * U, nkc = (bwd ? 3 * H : H) / 64;
     const long long w_chunk = (long long)N * 128;
     const long long budget = (long long)fn_max_smem_optin() - (long long)kSmemTail;
-    static const int ring_kb_f = env_int("FN_GRU_RING_KB", 96);        // state ring when the weights do not all fit
-    static const int wring_kb_f = env_int("FN_GRU_WRING_KB", 32);
-    static const int ring_kb_b = env_int("FN_GRU_RING_KB_BWD", ring_kb_f), wring_kb_b = env_int("FN_GRU_WRING_KB_BWD", wring_kb_f);
+    // state ring / weight ring when the weights do not all fit.  Defaults from the config-3 sweep (H = 1024, U = 32):
+    // the recurrent kernels are paced by the MMA-issuing warp's fixed cost per ring stage (~1000 cycles of waits,
+    // descriptor set-up and commits against 350-700 cycles of MMA execution), so FEWER, BIGGER stages win even though
+    // less of the weight slice stays resident: 64 KB stages (kch = 4), forward 128 + 96 KB (nothing resident),
+    // backward 160 + 32 KB.  The per-chunk rings of the greedy-decode kernel keep the earlier 96 / 32 KB.
+    static const int ring_kb_f = env_int("FN_GRU_RING_KB", slot_per_stage ? 128 : 96);
+    static const int wring_kb_f = env_int("FN_GRU_WRING_KB", slot_per_stage ? 96 : 32);
+    static const int ring_kb_b = env_int("FN_GRU_RING_KB_BWD", slot_per_stage ? 160 : ring_kb_f);
+    static const int wring_kb_b = env_int("FN_GRU_WRING_KB_BWD", slot_per_stage ? 32 : wring_kb_f);
     const int min_ring_kb = bwd ? ring_kb_b : ring_kb_f, wring_kb = bwd ? wring_kb_b : wring_kb_f;
-    pl.kch = (nkc % 2 == 0) ? 2 : 1;
+    int kch = kch_req;                                                  // K chunks (of 64) per ring stage
+    while (kch > 1 && nkc % kch) kch >>= 1;
+    pl.kch = kch;
+    const long long w_slot = slot_per_stage ? kch * w_chunk : w_chunk;  // bytes of one weight-ring slot
     long long room = budget - nkc * w_chunk;                            // ring space with a fully resident slice
     if (room >= 6LL * kATile) {
         pl.kres = nkc; pl.wst = 0;
     } else {
         // keep as much of the slice resident as leaves a >= min_ring_kb state ring + a small weight ring
-        int wst = (int)((wring_kb * 1024LL + w_chunk - 1) / w_chunk);
+        int wst = (int)((wring_kb * 1024LL + w_slot - 1) / w_slot);
         if (wst < 2) wst = 2;
         if (wst > kMaxWst) wst = kMaxWst;
-        long long kres = (budget - min_ring_kb * 1024LL - wst * w_chunk) / w_chunk;
-        if (kres > nkc - pl.kch) kres = nkc - pl.kch;
-        kres -= kres % pl.kch;                                          // streamed / resident parts in whole stages
+        if (!slot_per_stage && wst < kch) wst = kch;
+        long long kres = (budget - min_ring_kb * 1024LL - wst * w_slot) / w_chunk;
+        if (kres > nkc - kch) kres = nkc - kch;
+        kres -= kres % kch;                                             // streamed / resident parts in whole stages
         if (kres < 0) { pl.ok = false; return pl; }
         pl.kres = (int)kres; pl.wst = wst;
-        if (pl.wst < pl.kch) pl.wst = pl.kch;
-        room = budget - kres * w_chunk - pl.wst * w_chunk;
+        room = budget - kres * w_chunk - wst * w_slot;
     }
     long long tiles = room / kATile;                                    // 16 KB tiles available to the state ring
-    if (tiles < 4) pl.kch = 1;
+    if (!slot_per_stage && tiles < 4) pl.kch = 1;
     if (tiles > kMaxStages * pl.kch) tiles = kMaxStages * pl.kch;
     pl.stages = (int)(tiles / pl.kch);
     if (pl.stages > kMaxStages) pl.stages = kMaxStages;
     pl.ok = pl.stages >= 2;
     static const int verbose = env_int("FN_GRU_VERBOSE", 0);
-    if (verbose) fprintf(stderr, "tc_plan U=%d H=%d bwd=%d: kch=%d stages=%d kres=%d/%d wst=%d\n", U, H, (int)bwd, pl.kch, pl.stages, pl.kres, nkc, pl.wst);
-    pl.smem = (size_t)(pl.kres * w_chunk + pl.wst * w_chunk + (long long)pl.stages * pl.kch * kATile) + kSmemTail;
+    if (verbose && pl.ok) fprintf(stderr, "tc_plan U=%d H=%d bwd=%d: kch=%d stages=%d kres=%d/%d wst=%d (slots of %lld B)\n", U, H, (int)bwd, pl.kch, pl.stages, pl.kres, nkc, pl.wst, w_slot);
+    pl.smem = (size_t)(pl.kres * w_chunk + pl.wst * w_slot + (long long)pl.stages * pl.kch * kATile) + kSmemTail;
+    return pl;
+}
+
+TcPlan tc_plan(int U, int H, bool bwd, bool slot_per_stage = false) {
+    static const int kch_f = env_int("FN_GRU_KCH", 4), kch_b = env_int("FN_GRU_KCH_BWD", kch_f);
+    int kch = slot_per_stage ? (bwd ? kch_b : kch_f) : 2;
+    if (kch != 1 && kch != 2 && kch != 4) kch = 2;
+    TcPlan pl = tc_plan_k(U, H, bwd, slot_per_stage, kch);
+    while (!pl.ok && kch > 1 && slot_per_stage) pl = tc_plan_k(U, H, bwd, slot_per_stage, kch >>= 1);   // smaller stages fit more often
     return pl;
 }
 

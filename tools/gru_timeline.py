@@ -20,7 +20,7 @@ for c in range(NCH):
     k = 1 / math.sqrt(H)
     tensors += [(torch.randn(3 * H, V, generator=g) * k).to(dev).requires_grad_(True), (torch.randn(3 * H, generator=g) * k).to(dev).requires_grad_(True),
                 (torch.randn(3 * H, H, generator=g) * k).to(dev).requires_grad_(True), (torch.randn(3 * H, generator=g) * k).to(dev).requires_grad_(True)]
-dbg = torch.zeros((T + 1) * 2 * 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros((T + 1) * 2 * 64, dtype=torch.int64, device=dev)
 for it in range(2):
     (fin,) = GruGroupBf16Fn.apply(specs, B, T, H, (NCH * H,), *tensors)
 torch.cuda.synchronize()
@@ -32,7 +32,7 @@ e1.record()
 torch.cuda.synchronize()
 LIB.call("fn_gru_debug_timeline", None)
 print(f"forward launch (incl. setup kernels): {e0.elapsed_time(e1):.3f} ms = {e0.elapsed_time(e1) / T * 1e3:.2f} us/step")
-d = dbg.view(T + 1, 2, 16).cpu()
+d = dbg.view(T + 1, 2, 64).cpu()
 names = ["prod:start", "prod:flag seen", "prod:fenced", "prod:tma issued", "mma:first chunk", "mma:committed", "epi:arrive", "epi:acc ready",
          "epi:math done", "epi:stores issued", "epi:published"]
 nbt = (B + 127) // 128
@@ -40,6 +40,8 @@ for s in range(T // 2, min(T // 2 + 3, T)):
     for bt in range(nbt):
         t0 = int(d[s, bt, 0])
         print(f"step {s} bt {bt}: " + "  ".join(f"{names[k]}={int(d[s, bt, k]) - t0}" for k in range(1, 11)))
+        print(f"      mma warp: turn starts={int(d[s, bt, 11]) - t0} acc_empty seen={int(d[s, bt, 12]) - t0}  per stage (weights ready, state ready): "
+              + " ".join(f"({int(d[s, bt, 16 + 2 * j]) - t0},{int(d[s, bt, 17 + 2 * j]) - t0})" for j in range(min(12, H // 128))))
     if s + 1 < T:
         print(f"   step period (prod:start to next prod:start, bt0): {int(d[s + 1, 0, 0]) - int(d[s, 0, 0])} cycles")
 # backward timeline too
@@ -49,7 +51,7 @@ LIB.call("fn_gru_debug_timeline", _p(dbg))
 e0.record(); loss.backward(); e1.record(); torch.cuda.synchronize()
 LIB.call("fn_gru_debug_timeline", None)
 print(f"backward (incl. weight-gradient GEMMs): {e0.elapsed_time(e1):.3f} ms")
-d = dbg.view(T + 1, 2, 16).cpu()
+d = dbg.view(T + 1, 2, 64).cpu()
 for i in range(T // 2, min(T // 2 + 2, T)):
     for bt in range(nbt):
         t0 = int(d[i, bt, 0])

@@ -1,2 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "latent_block or softmax or clip_adam or nll" 2>&1 | tail -4
-timeout 600 python tools/bw_bench.py > gpurun_out/bw1.json 2> gpurun_out/bw1.err; tail -3 gpurun_out/bw1.err
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --breakdown 2>/dev/null | tail -1 > gpurun_out/c3_k.json
+python - <<'PY'
+import json,sys
+d=json.load(open("gpurun_out/c3_k.json")); b=d["breakdown_ms_per_step"]
+print("ms/step", d["ms_per_step"], "gru fwd", b["fn_gru_seq_fwd_bf16"][0], "bwd", b["fn_gru_seq_bwd_bf16"][0], d["last_step_outputs"])
+PY
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
