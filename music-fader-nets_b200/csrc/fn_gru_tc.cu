@@ -55,9 +55,9 @@ struct TcLaunch {
     unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
     long long* dbg;        // profiling aid (fn_gru_debug_timeline): [iteration][bt][16] clock64 stamps of CTA 0, or NULL
     int n_chains, nslices, B, T, H, stages, cluster;
+    int tsplit;            // CTAs per (chain, slice): each owns NBT of the chain's 128-row batch tiles (tsplit * NBT tiles)
     int kres, wst;         // resident K chunks of the weight slice; ring slots for the streamed rest (0 = all resident)
     int ls, lw;            // issuing warps of the state stream (1..4) and of the weight-tail stream (1..2)
-    int dbg_flags;         // profiling experiments only (FN_GRU_DBGFLAGS): 1 = skip the MMAs, 2 = skip the TMA loads
 };
 #define FN_STAMP(i, bt, k)                                                                       \
     do {                                                                                         \
@@ -69,7 +69,7 @@ struct TcLaunch {
 // =====================================================================================================
 template <int U, int NBT, bool BWD>
 __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& c, const Smem& sm, const uint32_t tmem_base, unsigned* gbar,
-                                              const int u0, const int warp, const int lane) {
+                                              const int u0, const int tile0, const int warp, const int lane) {
     constexpr int N = BWD ? U : 3 * U;
     constexpr uint32_t kAccCols = NBT * N;
     const int H = P.H, B = P.B, T = P.T;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
             // time-invariant part of the gate pre-activations -> TMEM columns [kAccCols + bt*N, +N)
 #pragma unroll
             for (int bt = 0; bt < NBT; ++bt) {
-                const int b = bt * 128 + q * 32 + lane;
+                const int b = (tile0 + bt) * 128 + q * 32 + lane;
                 const bool row_ok = b < B;
                 float pr[UT], pz[UT], pn[UT];
 #pragma unroll
@@ -121,7 +121,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                 const int tau_n = c.reverse ? tau - 1 : tau + 1;
 #pragma unroll
                 for (int bt = 0; bt < NBT; ++bt) {
-                    const int b = bt * 128 + q * 32 + lane;
+                    const int b = (tile0 + bt) * 128 + q * 32 + lane;
                     const bool row_ok = b < B;
                     const long long row_in = (long long)tau * B + b;       // input side is indexed by time
                     // ---- operand that does not depend on the recurrence: fetch before waiting for the MMA
@@ -162,7 +162,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     }
                     if (row_ok) stb<UT>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hreg[bt]);
                     if (stamp) FN_STAMP(s, bt, 9);
-                    if (s + 1 < T) publish(gbar + bt);               // the next step only needs the state
+                    if (s + 1 < T) publish(gbar + tile0 + bt);               // the next step only needs the state
                     if (stamp) FN_STAMP(s, bt, 10);
                     if (row_ok) {
                         if (c.gates) {                               // off the critical path: after the publish
@@ -187,10 +187,10 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
             const int grp = (warp - kEpiWarp0) >> 2;
             const int bt = NBT == 2 ? grp : 0;
             const int uu0 = NBT == 2 ? 0 : grp * UB;
-            const int b = bt * 128 + q * 32 + lane;
+            const int b = (tile0 + bt) * 128 + q * 32 + lane;
             const bool row_ok = b < B;
             const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(bt * N);
-            unsigned* gflag = gbar + bt;
+            unsigned* gflag = gbar + tile0 + bt;
             uint64_t* accf = &sm.acc_full[bt];
             uint64_t* acce = &sm.acc_empty[bt];
             float carry[UB];
@@ -230,10 +230,12 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     }
                 };
                 fetch(0);
+                if (stamp) FN_STAMP(i, bt, 6);
                 if (i > 0) {
                     tc::mbar_wait_warp(accf, (i - 1) & 1);
                     tc::tc_fence_after();
                 }
+                if (stamp) FN_STAMP(i, bt, 7);
                 float o_i[CH];
 #pragma unroll
                 for (int ch = 0; ch < NCHK; ++ch) {
@@ -275,7 +277,9 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     }
                 }
                 if (s < 0) continue;
+                if (stamp) FN_STAMP(i, bt, 9);
                 publish(gflag);                              // the recurrence consumes (dr, dz, dn*r) only
+                if (stamp) FN_STAMP(i, bt, 10);
                 if (NCHK == 1 && row_ok) stb<CH>(c.dg + row * 4 * H + u0 + uu0 + 2 * H, o_i);
             }
         }
@@ -308,18 +312,16 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;      // profiling stamps (fn_gru_debug_timeline)
-    const int chain = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
+    const int cta_group = blockIdx.x / P.nslices, slice = blockIdx.x % P.nslices;
+    const int chain = cta_group / P.tsplit, tile0 = (cta_group % P.tsplit) * NBT;   // first of this CTA's batch tiles
     const TcChain& c = P.c[chain];
     unsigned* gbar = P.bar + chain * 16;
     const int u0 = slice * U;
-    // cluster = `csize` consecutive slices of one chain: each streams 1/csize of every state tile and multicasts it
-    const uint32_t crank = tc::cluster_ctarank(), csize = tc::cluster_nctarank();
-    const uint16_t cmask = (uint16_t)((1u << csize) - 1);
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&c.tmW);
         tc::prefetch_tmap(&c.tmA);
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], csize); }
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], 1); }
         for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], BWD ? kEpiWarps / NBT : kEpiWarps); }
         tc::mbar_init(sm.wbar, 1);
         for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
@@ -331,7 +333,6 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
     }
     tc::tc_fence_before();
     __syncthreads();
-    tc::cluster_sync();                                        // peers' barriers are initialised before any remote arrive
     tc::tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
     const int lrank = state_loader_rank(warp), trank = tail_loader_rank(warp);
@@ -359,11 +360,8 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         {
             // ---- state-slab stream.  One thread, so everything per stage is kept to a handful of instructions:
             // raw shared addresses, incremental stage / phase / column counters, no divisions.
-            const uint32_t rows = 128u / csize;                                   // tmA's box is 64 x rows
-            const uint32_t a0 = tc::smem_u32(sm.A) + crank * rows * 128u;
+            const uint32_t a0 = tc::smem_u32(sm.A);
             const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
-            const int row0 = (int)(crank * rows);
-            const bool mc = csize > 1, skip_tma = (P.dbg_flags & 2) != 0;
             const int nst = nkc / KCH;                                            // stages per (step, batch tile)
             uint32_t st = 0, ph = 1;                                              // ph: parity that means "slot free"
             int turn = 0;                                                         // stages are dealt round-robin to the loaders
@@ -374,7 +372,7 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
                 for (int bt = 0; bt < NBT; ++bt) {
                     if (lrank == 0) FN_STAMP(i, bt, 0);
                     if (i > 0) {
-                        fn_spin_until(gbar + bt, (unsigned)(P.nslices * i) * (BWD ? kEpiWarps / NBT : kEpiWarps));
+                        fn_spin_until(gbar + tile0 + bt, (unsigned)(P.nslices * i) * (BWD ? kEpiWarps / NBT : kEpiWarps));
                         if (lrank == 0) FN_STAMP(i, bt, 1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
@@ -386,18 +384,13 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
                         const bool mine = (turn == lrank);
                         if (mine) tc::mbar_wait_u32(empty0 + st * 8u, ph);
                         if (mine && tc::elect_one()) {
-                            if (skip_tma) {
-                                tc::mbar_arrive_u32(fb);
-                            } else {
-                                tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
+                            tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
 #pragma unroll
-                                for (int q = 0; q < KCH; ++q) {
-                                    // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
-                                    const int cq = col + q * 64;
-                                    const int cc = (BWD && cq >= 2 * H) ? cq + H : cq;
-                                    if (mc) tc::tma_load_3d_mc_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128 + row0, slab, cmask);
-                                    else tc::tma_load_3d_u32(sa + q * kATile, &c.tmA, fb, cc, bt * 128, slab);
-                                }
+                            for (int q = 0; q < KCH; ++q) {
+                                // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
+                                const int cq = col + q * 64;
+                                const int cc = (BWD && cq >= 2 * H) ? cq + H : cq;
+                                tc::tma_load_3d_u32(sa + q * kATile, &c.tmA, fb, cc, (tile0 + bt) * 128, slab);
                             }
                         }
                         __syncwarp();
@@ -411,64 +404,65 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         }
     };
     auto mma_role = [&]() {
-        {
-            const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
-            tc::mbar_wait(sm.wbar, 0);
-            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
-            const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
-            const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
-            const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
-            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
-            uint32_t ws = 0, wph = 0;
-            const uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4;   // descriptor address units (16 B)
-            const bool mc = csize > 1, skip_mma = (P.dbg_flags & 1) != 0;
-            const int nst = nkc / KCH;
-            uint32_t st = 0, ph = 0, uses = 0;
-            for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
-                for (int bt = 0; bt < NBT; ++bt) {
-                    FN_STAMP(i, bt, 11);
-                    tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
+        // This single-thread loop paces the whole kernel (ncu: ~1500 cycles per 64 KB stage against ~700 cycles of MMA
+        // execution), so it is kept to the bare sequence wait -> MMAs -> commits: the streamed and the resident stages
+        // are separate loops (no per-MMA selects), descriptors advance by constants, no profiling code inside.
+        const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+        tc::mbar_wait(sm.wbar, 0);
+        const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
+        const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
+        const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
+        const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
+        const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+        constexpr uint32_t a_step = stage_bytes >> 4;                          // descriptor address units (16 B)
+        const uint32_t b_step = (uint32_t)w_chunk_bytes >> 4, slot_step = KCH * b_step;
+        const int nst = nkc / KCH, nsst = nstream / KCH;                       // stages per (step, tile); streamed ones first
+        uint32_t st = 0, ph = 0, ws = 0, wph = 0, uses = 0;
+        // one stage: KCH chunks x 4 MMAs (K = 16 each); `first` clears the accumulator with the very first MMA
+        auto issue = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, bool first) {
+#pragma unroll
+            for (int q = 0; q < KCH; ++q) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bd + (uint64_t)(q * b_step + 2 * k), idesc,
+                                 (q | k) ? 1u : (first ? 0u : 1u));
+            }
+        };
+        for (int i = BWD ? 1 : 0; i < n_iters; ++i, ++uses) {
+            for (int bt = 0; bt < NBT; ++bt) {
+                tc::mbar_wait(&sm.acc_empty[bt], (uses & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
+                for (int j = 0; j < nsst; ++j) {                               // weights from the tail ring
+                    tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
+                    tc::mbar_wait_u32(full0 + st * 8u, ph);
                     tc::tc_fence_after();
-                    FN_STAMP(i, bt, 12);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(bt * N);
-                    uint64_t bd = bdesc0;
-                    for (int j = 0; j < nst; ++j) {
-                        const bool streamed = j * KCH < nstream;
-                        // streamed weight chunks of this stage (one tail-ring slot): wait for them
-                        uint32_t wsl = 0;
-                        if (streamed) {
-                            tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
-                            wsl = ws;
-                            if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
-                        }
-                        if (j < 12) FN_STAMP(i, bt, 16 + 2 * j);          // weight chunks of the stage present
-                        tc::mbar_wait_u32(full0 + st * 8u, ph);
-                        tc::tc_fence_after();
-                        if (j == 0) FN_STAMP(i, bt, 4);
-                        if (j < 12) FN_STAMP(i, bt, 17 + 2 * j);          // state chunks of the stage present
-                        const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
-                        if (tc::elect_one()) {
-#pragma unroll
-                            for (int q = 0; q < KCH; ++q) {
-                                const uint64_t bq = streamed ? wdesc0 + (uint64_t)((wsl * KCH + q) * b_step) : bd + (uint64_t)(q * b_step);
-                                if (!skip_mma) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bq + (uint64_t)(2 * k), idesc,
-                                                     (uint32_t)((j | q | k) != 0));
-                                }
-                            }
-                            if (streamed) tc::umma_commit_u32(wempty0 + wsl * 8u);              // weight-ring slot reusable
-                            if (mc) tc::umma_commit_mc_u32(empty0 + st * 8u, cmask);  // frees the slot in every CTA that fills it
-                            else tc::umma_commit_u32(empty0 + st * 8u);
-                            if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
-                        }
-                        __syncwarp();
-                        if (!streamed) bd += (uint64_t)KCH * b_step;
-                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                    if (j == 0) FN_STAMP(i, bt, 4);
+                    if (tc::elect_one()) {
+                        issue(d_tmem, adesc0 + (uint64_t)(st * a_step), wdesc0 + (uint64_t)(ws * slot_step), j == 0);
+                        tc::umma_commit_u32(wempty0 + ws * 8u);                // weight-ring slot reusable
+                        tc::umma_commit_u32(empty0 + st * 8u);                 // state-ring slot reusable
+                        if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
                     }
-                    FN_STAMP(i, bt, 5);
+                    __syncwarp();
+                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                 }
+                uint64_t bd = bdesc0;
+                for (int j = nsst; j < nst; ++j) {                             // resident weights
+                    tc::mbar_wait_u32(full0 + st * 8u, ph);
+                    tc::tc_fence_after();
+                    if (j == 0) FN_STAMP(i, bt, 4);
+                    if (tc::elect_one()) {
+                        issue(d_tmem, adesc0 + (uint64_t)(st * a_step), bd, j == 0);
+                        tc::umma_commit_u32(empty0 + st * 8u);
+                        if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
+                    }
+                    __syncwarp();
+                    bd += (uint64_t)slot_step;
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                }
+                FN_STAMP(i, bt, 5);
             }
         }
     };
@@ -508,7 +502,7 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         }
     };
 
-    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + (int)kEpiWarps) epilogue_role<U, NBT, BWD>(P, c, sm, tmem_base, gbar, u0, warp, lane);
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + (int)kEpiWarps) epilogue_role<U, NBT, BWD>(P, c, sm, tmem_base, gbar, u0, tile0, warp, lane);
     else if (warp == 1) mma_role();
     else if (lrank >= 0 && lrank < P.ls) state_loader_role();
     else if (trank >= 0 && trank < P.lw) tail_loader_role();
@@ -517,7 +511,6 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, kTmemCols);
     }
-    tc::cluster_sync();                                        // no CTA leaves while peers may still signal its barriers
 }
 
 // ---- host -------------------------------------------------------------------------------------------
@@ -543,7 +536,7 @@ int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(P.n_chains * P.nslices);
+    cfg.gridDim = dim3(P.n_chains * P.tsplit * P.nslices);
     cfg.blockDim = dim3(kThreadsGru);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -557,8 +550,8 @@ int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
     // all CTAs must be resident at once (slices of a chain wait for each other every step)
     int max_clusters = 0;
     FN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
-    FN_REQUIRE(max_clusters * P.cluster >= P.n_chains * P.nslices,
-               "fn_gru_seq_bf16: %d CTAs in clusters of %d are not co-resident (max %d clusters)", P.n_chains * P.nslices,
+    FN_REQUIRE(max_clusters * P.cluster >= P.n_chains * P.tsplit * P.nslices,
+               "fn_gru_seq_bf16: %d CTAs in clusters of %d are not co-resident (max %d clusters)", P.n_chains * P.tsplit * P.nslices,
                P.cluster, max_clusters);
     void* args[] = {(void*)&P};
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
@@ -572,6 +565,9 @@ int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
 }
 template <bool BWD, int KCH>
 int dispatch_tc2(int U, int nbt, const TcLaunch& P, size_t smem, cudaStream_t st) {
+    if constexpr (BWD) {
+        if (U == 64) return launch_tc<64, 1, BWD, KCH>(P, smem, st);      // tile-split BPTT only (see run_tc)
+    }
     if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD, KCH>(P, smem, st) : launch_tc<32, 2, BWD, KCH>(P, smem, st);
     return nbt == 1 ? launch_tc<16, 1, BWD, KCH>(P, smem, st) : launch_tc<16, 2, BWD, KCH>(P, smem, st);
 }
@@ -590,18 +586,27 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
     FN_REQUIRE(barrier_ws && ws_bytes >= (size_t)64 * n_chains, "fn_gru_seq_bf16: barrier_ws too small");
     FN_CHECK_CUDA(cudaMemsetAsync(barrier_ws, 0, (size_t)64 * n_chains, st));
     const int nbt = (B + 127) / 128;
-    static const int force_cs = getenv("FN_GRU_CLUSTER") ? atoi(getenv("FN_GRU_CLUSTER")) : 0;
     int done = 0;
     while (done < n_chains) {
         int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc, U = 0;
         for (; group >= 1; --group)
             if ((U = pick_u_tc(group, H)) != 0) break;
         FN_REQUIRE(group >= 1, "fn_gru_seq_bf16: H=%d not supported by the tcgen05 path", H);
+        // BPTT, tile split: the product has N = U columns and tcgen05.mma costs >= ~43 cycles whatever N <= 64 (it is
+        // bound by the 4 KB A-tile read), so 64-unit slices double the work per MMA; each CTA then takes ONE 128-row
+        // batch tile of its chain (half the MMAs and ring stages per step for the MMA-issuing warp that paces the
+        // kernel) and the CTA count stays n_chains * (H / 32).
+        static const int tsplit_env = env_int("FN_GRU_TSPLIT", 1);
+        int tsplit = 1, nbt_cta = nbt;
+        if (bwd && tsplit_env && nbt == 2 && H % 64 == 0 && tc_plan(64, H, true, true).ok &&
+            (long long)group * (H / 64) * nbt <= fn_num_sms()) {
+            U = 64; tsplit = nbt; nbt_cta = 1;
+        }
         TcLaunch P;
         memset(&P, 0, sizeof(P));
-        // cluster of consecutive slices that share (multicast) the streamed state tiles
-        int cs = force_cs ? force_cs : 1;     // multicast sharing measured neutral on B200 (delivery to the SM, not L2 reads, is the bound): off by default
-        while (cs > 1 && ((H / U) % cs != 0 || 128 % cs != 0)) cs >>= 1;
+        // (cluster multicast of the state tiles between slices of a chain was implemented and measured neutral at 2, 4
+        // and 8 CTAs per cluster -- the MMA-issue loop, not L2 reads, paces the kernel -- and removed.)
+        const int cs = 1;
         P.cluster = cs;
         for (int i = 0; i < group; ++i) {
             const FnGruChainBf16& s = chains[done + i];
@@ -632,7 +637,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
             d.reverse = s.reverse; d.dhs_f32 = s.dhs_f32;
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
-        P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H;
+        P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H; P.tsplit = tsplit;
         const TcPlan pl = tc_plan(U, H, bwd, true);
         const int kch = pl.kch;
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
@@ -646,9 +651,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         while (P.stages % P.ls) --P.ls;
         while (P.wst > 0 && P.wst % P.lw) --P.lw;
         P.dbg = g_dbg;
-        static const int dbg_flags = getenv("FN_GRU_DBGFLAGS") ? atoi(getenv("FN_GRU_DBGFLAGS")) : 0;
-        P.dbg_flags = dbg_flags;
-        const int rc = bwd ? dispatch_tc<true>(U, nbt, kch, P, pl.smem, st) : dispatch_tc<false>(U, nbt, kch, P, pl.smem, st);
+        const int rc = bwd ? dispatch_tc<true>(U, nbt_cta, kch, P, pl.smem, st) : dispatch_tc<false>(U, nbt_cta, kch, P, pl.smem, st);
         if (rc != FN_OK) return rc;
         done += group;
     }

@@ -55,5 +55,5 @@ d = dbg.view(T + 1, 2, 64).cpu()
 for i in range(T // 2, min(T // 2 + 2, T)):
     for bt in range(nbt):
         t0 = int(d[i, bt, 0])
-        print(f"bwd iter {i} bt {bt}: " + "  ".join(f"{names[k]}={int(d[i, bt, k]) - t0}" for k in range(1, 6)))
+        print(f"bwd iter {i} bt {bt}: " + "  ".join(f"{names[k]}={int(d[i, bt, k]) - t0}" for k in (1, 2, 3, 4, 5, 6, 7, 9, 10)))
     print(f"   iter period: {int(d[i + 1, 0, 0]) - int(d[i, 0, 0])} cycles")

@@ -1,7 +1,9 @@
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --breakdown 2>/dev/null | tail -1 > gpurun_out/c3_k.json
-python - <<'PY'
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for w in c2_bf16 c5 c2; do
+timeout 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/b_$w.json
+python - $w <<'PY'
 import json,sys
-d=json.load(open("gpurun_out/c3_k.json")); b=d["breakdown_ms_per_step"]
-print("ms/step", d["ms_per_step"], "gru fwd", b["fn_gru_seq_fwd_bf16"][0], "bwd", b["fn_gru_seq_bwd_bf16"][0], d["last_step_outputs"])
+d=json.load(open("gpurun_out/b_%s.json" % sys.argv[1]))
+print(sys.argv[1], d["metric"], d["value"], d["unit"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"])
 PY
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+done
