@@ -1,0 +1,60 @@
+"""Turns the raw ncu outputs of tools/profile.sh (gpurun_out/) into the tracked summaries under profiles/.
+usage: python tools/summarize_profiles.py rNN"""
+import csv, io, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+# ---- launch list (ncu --metrics gpu__time_duration.sum --csv): per-kernel totals of the LAST train step ---------------
+src = os.path.join(G, f"{tag}_launches_c3_bf16.csv")
+if os.path.exists(src):
+    lines = [l for l in open(src, errors="replace") if l.startswith('"')]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    recs = [(r["Kernel Name"], float(r["Metric Value"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r["Metric Unit"], 1e-3))
+            for r in rows if r.get("Metric Name") == "gpu__time_duration.sum"]
+    # one step = the launches after the last clip_adam of the warm-up step
+    idx = [i for i, (n, _) in enumerate(recs) if "clip_adam" in n]
+    step = recs[idx[-2] + 1: idx[-1] + 1] if len(idx) >= 2 else recs
+    tot = sum(t for _, t in step)
+    agg = {}
+    for n, t in step:
+        a = agg.setdefault(n, [0.0, 0]); a[0] += t; a[1] += 1
+    with open(os.path.join(P, f"{tag}_launches_c3_bf16.txt"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --workload c3 --steps 1 --warmup 1 --no-cpu-baseline\n")
+        f.write(f"# {tag}, bf16 tensor-core path, B=256 T=512 H=1024: the {len(step)} launches of ONE train step (between two clip_adam launches);\n")
+        f.write("# per-launch times under ncu are serialised and cold-cache: compare SHARES, not absolutes\n")
+        f.write(f"# total {tot:.1f} us\n")
+        for n, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{t:12.1f} us {100 * t / tot:6.2f}% n={c:4d} {n[:150]}\n")
+    with open(os.path.join(P, f"{tag}_launches_c3_bf16.csv"), "w") as f:
+        f.write("kernel,us\n")
+        for n, t in step: f.write(f'"{n}",{t:.3f}\n')
+    print("launch list:", len(step), "launches,", round(tot / 1e3, 2), "ms")
+
+# ---- full capture of the GRU kernels -------------------------------------------------------------------------------
+rep = os.path.join(G, f"{tag}_gru_tc_c3.ncu-rep")
+if os.path.exists(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    h, units = rows[0], rows[1]
+    keep = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+    traffic = 0.0
+    with open(os.path.join(P, f"{tag}_ncu_gru_tc_c3_bf16.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none, bench.py --workload c3 (B=256,T=512,H=1024,bf16): the {len(rows) - 2} gru_tc_kernel launches of ONE train step\n")
+        for r in rows[2:]:
+            f.write(f"--- {r[h.index('Kernel Name')][:110]}\n")
+            for k in keep:
+                if k in h: f.write(f"{k:84s} {r[h.index(k)]:>16s} {units[h.index(k)]}\n")
+            def gb(k):
+                v, u = float(r[h.index(k)]), units[h.index(k)]
+                return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[u]
+            traffic += gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+    tj = os.path.join(P, f"{tag}_traffic.json")
+    d = json.load(open(tj)) if os.path.exists(tj) else {}
+    d["c3"] = int(traffic)
+    json.dump(d, open(tj, "w"))
+    print("GRU kernels:", len(rows) - 2, "launches, DRAM traffic per step", round(traffic / 1e9, 2), "GB")
