@@ -14,6 +14,19 @@ import json
 import os
 import subprocess
 import sys
+
+# stdout carries exactly ONE JSON line.  Libraries write banners to the C-level stdout (NCCL / c10d print
+# "NCCL version ..." when the first communicator is created), so file descriptor 1 is pointed at stderr for the whole
+# run and the JSON line goes to a private duplicate of the original stdout.
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 import threading
 import time
 
@@ -275,7 +288,7 @@ def run_ours(args):
         line["breakdown_ms_per_step"] = breakdown       # C-ABI call -> [ms per step, calls per step] (event-timed, serial)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference(args.workload, steps=1, warmup=1)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -347,7 +360,7 @@ def run_decode(args):
                              "achieved": round(fl / (sec / n) / 1e12, 3), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                              "frac": round(fl / (sec / n) / 1e12 / peaks["tf_sust"], 5), "traffic": None},
                 "tokens_head": toks[0, :8].tolist()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -395,7 +408,7 @@ def run_reference(args):
                        "note": "reference algorithm (fp32, dense one-hot GEMMs) on the host cores; bounded sample, see cpu_baseline.sample"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
