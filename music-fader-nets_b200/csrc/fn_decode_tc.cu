@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) decode_tc_kernel(const __grid_c
     constexpr int w_chunk_bytes = kN * 128;
     constexpr uint32_t stage_bytes = KCH * kATile;
     const int kres = P.kres, nstream = nkc - kres, WST = P.wst;
-    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * w_chunk_bytes, S * KCH);
+    const Smem sm = carve(smem_raw, kres * w_chunk_bytes, WST * KCH * w_chunk_bytes, S * KCH);   // a weight-ring slot = the KCH chunks of one stage
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int role = 0;
@@ -143,44 +143,50 @@ __global__ void __launch_bounds__(kThreadsTc, 1) decode_tc_kernel(const __grid_c
         const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
         const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
         const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
-        const uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4;
-        const int nst = nkc / KCH;
+        constexpr uint32_t a_step = stage_bytes >> 4, b_step = (uint32_t)w_chunk_bytes >> 4, slot_step = KCH * b_step;
+        const int nst = nkc / KCH, nsst = nstream / KCH;        // stages per (step, tile); the streamed ones come first
         uint32_t st = 0, ph = 0, ws = 0, wph = 0;
+        // same bare wait -> MMAs -> commits sequence as the training kernel (fn_gru_tc.cu): this single-thread loop
+        // paces the role
+        auto issue = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, bool first) {
+#pragma unroll
+            for (int q = 0; q < KCH; ++q) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bd + (uint64_t)(q * b_step + 2 * k), idesc,
+                                 (q | k) ? 1u : (first ? 0u : 1u));
+            }
+        };
         for (int s = 0; s < T; ++s) {
             for (int bt = 0; bt < NBT; ++bt) {
                 tc::mbar_wait(&sm.acc_empty[bt], (s & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(bt * kN);
-                uint64_t bd = bdesc0;
-                for (int j = 0; j < nst; ++j) {
-                    const bool streamed = j * KCH < nstream;
-                    uint32_t wslot[KCH];
-                    if (streamed) {
-#pragma unroll
-                        for (int q = 0; q < KCH; ++q) {
-                            tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
-                            wslot[q] = ws;
-                            if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
-                        }
-                    }
+                for (int j = 0; j < nsst; ++j) {                 // weights from the tail ring
+                    tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
                     tc::mbar_wait_u32(full0 + st * 8u, ph);
                     tc::tc_fence_after();
-                    const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
                     if (tc::elect_one()) {
-#pragma unroll
-                        for (int q = 0; q < KCH; ++q) {
-                            const uint64_t bq = streamed ? wdesc0 + (uint64_t)(wslot[q] * b_step) : bd + (uint64_t)(q * b_step);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc::umma_f16(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bq + (uint64_t)(2 * k), idesc,
-                                             (uint32_t)((j | q | k) != 0));
-                            if (streamed) tc::umma_commit_u32(wempty0 + wslot[q] * 8u);
-                        }
+                        issue(d_tmem, adesc0 + (uint64_t)(st * a_step), wdesc0 + (uint64_t)(ws * slot_step), j == 0);
+                        tc::umma_commit_u32(wempty0 + ws * 8u);
                         tc::umma_commit_u32(empty0 + st * 8u);
                         if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
                     }
                     __syncwarp();
-                    if (!streamed) bd += (uint64_t)KCH * b_step;
+                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                }
+                uint64_t bd = bdesc0;
+                for (int j = nsst; j < nst; ++j) {               // resident weights
+                    tc::mbar_wait_u32(full0 + st * 8u, ph);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        issue(d_tmem, adesc0 + (uint64_t)(st * a_step), bd, j == 0);
+                        tc::umma_commit_u32(empty0 + st * 8u);
+                        if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
+                    }
+                    __syncwarp();
+                    bd += (uint64_t)slot_step;
                     if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                 }
             }
@@ -189,16 +195,22 @@ __global__ void __launch_bounds__(kThreadsTc, 1) decode_tc_kernel(const __grid_c
         // ------------------------------- streamed part of the weight slice ----------------------------
         if (nstream > 0) {
             const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+            constexpr uint32_t slot_bytes = (uint32_t)(KCH * w_chunk_bytes);
+            const int nsst = nstream / KCH;
             uint32_t ws = 0, wph = 1;
             for (int ts = 0; ts < T * NBT; ++ts) {
-                for (int pch = 0; pch < nstream; ++pch) {
+                for (int pst = 0; pst < nsst; ++pst) {
                     tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
                     if (tc::elect_one()) {
-                        const uint32_t dst = wr0 + ws * (uint32_t)w_chunk_bytes, fb = wfull0 + ws * 8u;
-                        tc::mbar_arrive_expect_tx_u32(fb, (uint32_t)w_chunk_bytes);
+                        const uint32_t dst = wr0 + ws * slot_bytes, fb = wfull0 + ws * 8u;
+                        tc::mbar_arrive_expect_tx_u32(fb, slot_bytes);
 #pragma unroll
-                        for (int g = 0; g < 3; ++g)
-                            tc::tma_load_2d_u32(dst + g * kU * 128, &R.tmW, fb, (kres + pch) * 64, wrow0 + g * R.w_gate_stride);
+                        for (int q = 0; q < KCH; ++q) {
+#pragma unroll
+                            for (int g = 0; g < 3; ++g)
+                                tc::tma_load_2d_u32(dst + q * w_chunk_bytes + g * kU * 128, &R.tmW, fb, (kres + pst * KCH + q) * 64,
+                                                    wrow0 + g * R.w_gate_stride);
+                        }
                     }
                     __syncwarp();
                     if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
@@ -412,7 +424,7 @@ extern "C" int fn_decode_greedy_bf16(const void* w_hh1, const float* b_hh1, cons
                "fn_decode_greedy_bf16: need B <= 256, H %% 64 == 0 (B=%d H=%d)", B, H);
     FN_REQUIRE(ws_bytes >= fn_decode_greedy_ws_bytes(B, steps, H, V), "fn_decode_greedy_bf16: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    const TcPlan pl = tc_plan(kU, H, false);
+    const TcPlan pl = tc_plan(kU, H, false, true);
     FN_REQUIRE(pl.ok, "fn_decode_greedy_bf16: H=%d does not fit", H);
     DecLaunch P;
     memset(&P, 0, sizeof(P));
@@ -459,7 +471,8 @@ extern "C" int fn_decode_greedy_bf16(const void* w_hh1, const float* b_hh1, cons
     P.b_out = b_out; P.logits_out = logits_out;
     const int nbt = (B + 127) / 128;
     int rc;
-    if (pl.kch == 2) rc = nbt == 1 ? launch_dec<1, 2>(P, cta, pl.smem, st) : launch_dec<2, 2>(P, cta, pl.smem, st);
+    if (pl.kch == 4) rc = nbt == 1 ? launch_dec<1, 4>(P, cta, pl.smem, st) : launch_dec<2, 4>(P, cta, pl.smem, st);
+    else if (pl.kch == 2) rc = nbt == 1 ? launch_dec<1, 2>(P, cta, pl.smem, st) : launch_dec<2, 2>(P, cta, pl.smem, st);
     else rc = nbt == 1 ? launch_dec<1, 1>(P, cta, pl.smem, st) : launch_dec<2, 1>(P, cta, pl.smem, st);
     if (rc != FN_OK) return rc;
     decode_tokens_kernel<<<fn_cdiv((long long)steps * B, 256), 256, 0, st>>>(P.pval, P.pidx, steps, P.npart, B, tokens);
