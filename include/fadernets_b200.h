@@ -146,7 +146,11 @@ typedef struct FnGruChainBf16 {
     int32_t reverse;
     int32_t dhs_f32;          /* dtype of dhs: 0 = bf16, 1 = fp32                             */
     void* hsx;                /* bf16 [T+1][B][H] (see above)                                 */
-    void* gates;              /* bf16 [T][B][4H]: r, z, n, W_hn h + b_hn  (NULL = inference)  */
+    void* gates;              /* bf16, T * ceil32(B) * 4H elements: r, z, n, W_hn h + b_hn saved for BPTT (NULL =
+                               * inference).  OPAQUE to the caller: written by fn_gru_seq_fwd_bf16, read by
+                               * fn_gru_seq_bwd_bf16, stored in [32 rows][16 columns] blocks (block order: time slab,
+                               * 32-row block, 16-column block) so that the gate epilogues access it coalesced.  A time
+                               * segment [t0, t0+L) starts at element offset t0 * ceil32(B) * 4H.               */
     float* h_final;           /* fp32 rows of stride h_final_ld: state after the last step / NULL */
     long long h_final_ld;
     const void* dhs;          /* [T][B][H] by time: grad wrt h_tau, or NULL                   */

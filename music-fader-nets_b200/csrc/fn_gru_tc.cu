@@ -39,16 +39,31 @@ struct TcChain {
     int reverse, dhs_f32;
 };
 
-// Warp roles (15 warps): warp 0 = state loader 0 (+ resident weights), warp 1 = MMA issuer, warps 2-3 = state loaders 1-2,
+// Warp roles (15 warps; 23 in the tile-split BPTT, see Roles): warp 0 = state loader 0 (+ resident weights), warp 1 = MMA issuer, warps 2-3 = state loaders 1-2,
 // warps 4-11 = the 8 gate-epilogue warps, warp 12 = state loader 3, warps 13-14 = weight-tail loaders 0-1.
 // A single issuing warp sustains only ~30 B/clk of TMA ingest on B200 (tools/ubench_tc.cu: 30 / 73 / 110 / 126 B/clk
 // per SM with 1 / 2 / 3 / 4 issuing warps), so the ring stages are dealt round-robin to several loader warps.
 // (setmaxnreg re-balancing between warpgroups was tried: ptxas then spills in the 80-register control roles.)
-constexpr int kThreadsGru = 480;
 constexpr int kEpiWarp0 = 4;
+// Epilogue warps of an instantiation: 8, or 16 for the tile-split BPTT (64-unit slices, one batch tile per CTA): there a
+// thread then owns ONE 16-unit chunk of its row and fetches all of its saved gates before the accumulator is ready; with
+// 8 warps the second chunk's loads sat on the step's critical path (gate-gradient epilogue 8.4k of the 30k-cycle step).
+template <int U, int NBT, bool BWD> struct Roles {
+    static constexpr int kEpi = (BWD && U == 64 && NBT == 1) ? 16 : 8;       // epilogue warps 4 .. 4 + kEpi - 1
+    // 8 epilogue warps: + state loader 3 and tail loaders 0-1 after them (15 warps, 128 registers per thread).
+    // 16 epilogue warps: no optional loaders, the tail loader is warp 2 (20 warps, 96 registers per thread).
+    static constexpr bool kLean = kEpi == 16;
+    static constexpr int kWarps = kLean ? kEpiWarp0 + kEpi : kEpiWarp0 + kEpi + 3;
+    static constexpr int kThreads = kWarps * 32;
+};
 constexpr int kMaxStateLoaders = 4, kMaxTailLoaders = 2;
-__device__ __forceinline__ int state_loader_rank(int warp) { return warp == 0 ? 0 : warp == 2 ? 1 : warp == 3 ? 2 : warp == 12 ? 3 : -1; }
-__device__ __forceinline__ int tail_loader_rank(int warp) { return warp == 13 ? 0 : warp == 14 ? 1 : -1; }
+// `after` = first warp after the epilogue warps; lean = the 20-warp layout without optional loaders
+__device__ __forceinline__ int state_loader_rank(int warp, int after, bool lean) {
+    return warp == 0 ? 0 : lean ? -1 : warp == 2 ? 1 : warp == 3 ? 2 : warp == after ? 3 : -1;
+}
+__device__ __forceinline__ int tail_loader_rank(int warp, int after, bool lean) {
+    return lean ? (warp == 2 ? 0 : -1) : warp == after + 1 ? 0 : warp == after + 2 ? 1 : -1;
+}
 
 struct TcLaunch {
     TcChain c[kMaxChainsTc];
@@ -67,11 +82,21 @@ struct TcLaunch {
 // =====================================================================================================
 // Gate epilogue (8 warps, two warpgroups), see the kernel header below.
 // =====================================================================================================
+// The saved gates are private to the forward / backward kernels, so they are stored in [32 rows][16 columns] blocks
+// (1 KB; block order: time slab, 32-row block, 16-column block) instead of [T][B][4H] rows: a warp of the epilogue owns
+// 32 consecutive rows x 16 (or 8) consecutive units, i.e. exactly one block per gate, so its loads and stores are
+// contiguous 512-1024 B instead of 32 sectors 8 KB apart (the epilogues are LSU-transaction bound).
+__device__ __forceinline__ long long gate_off(long long t, int b, int col, int B, int H4) {
+    const long long row_blocks = (B + 31) >> 5;
+    return ((t * row_blocks + (b >> 5)) * (long long)(H4 >> 4) + (col >> 4)) * 512 + (b & 31) * 16 + (col & 15);
+}
+
 template <int U, int NBT, bool BWD>
 __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& c, const Smem& sm, const uint32_t tmem_base, unsigned* gbar,
                                               const int u0, const int tile0, const int warp, const int lane) {
     constexpr int N = BWD ? U : 3 * U;
     constexpr uint32_t kAccCols = NBT * N;
+    constexpr int EW = Roles<U, NBT, BWD>::kEpi;
     const int H = P.H, B = P.B, T = P.T;
     const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     {
@@ -166,8 +191,10 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     if (stamp) FN_STAMP(s, bt, 10);
                     if (row_ok) {
                         if (c.gates) {                               // off the critical path: after the publish
-                            __nv_bfloat16* gsv = c.gates + row_in * 4 * H + u;
-                            stb<UT>(gsv, r); stb<UT>(gsv + H, z); stb<UT>(gsv + 2 * H, n); stb<UT>(gsv + 3 * H, g);
+                            stb<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), r);
+                            stb<UT>(c.gates + gate_off(tau, b, H + u, B, 4 * H), z);
+                            stb<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, 4 * H), n);
+                            stb<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, 4 * H), g);
                         }
                         if (s == T - 1 && c.h_final) {               // caller-chosen offset / pitch: no alignment assumed
                             float* hf = c.h_final + (long long)b * c.h_final_ld + u;
@@ -181,12 +208,13 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
             // Backward: the epilogue is load-heavy (saved gates, states, incoming gradients), so the two warp groups
             // each OWN one batch tile (all U units of a row per thread, in register chunks of CH) and run
             // concurrently instead of serving the tiles one after the other.
-            constexpr int UB = (NBT == 2) ? U : U / 2;
+            constexpr int UB = U * NBT / (EW / 4);                  // units per thread: EW/4 warp groups over NBT tiles x U units
             constexpr int CH = UB > 16 ? 16 : UB;
             constexpr int NCHK = UB / CH;
             const int grp = (warp - kEpiWarp0) >> 2;
             const int bt = NBT == 2 ? grp : 0;
             const int uu0 = NBT == 2 ? 0 : grp * UB;
+            static_assert(NBT == 1 || EW == 8, "two tiles per CTA: one 4-warp group per tile");
             const int b = (tile0 + bt) * 128 + q * 32 + lane;
             const bool row_ok = b < B;
             const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)(bt * N);
@@ -210,9 +238,10 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
 #pragma unroll
                     for (int j = 0; j < CH; ++j) din[j] = 0.f;
                     if (row_ok && s >= 0) {
-                        const __nv_bfloat16* gsv = c.gates + row * 4 * H + uc;
-                        ldb_raw<CH>(gsv, wr, false); ldb_raw<CH>(gsv + H, wz, false);
-                        ldb_raw<CH>(gsv + 2 * H, wn, false); ldb_raw<CH>(gsv + 3 * H, wg, false);
+                        ldb_raw<CH>(c.gates + gate_off(tau, b, uc, B, 4 * H), wr, false);
+                        ldb_raw<CH>(c.gates + gate_off(tau, b, H + uc, B, 4 * H), wz, false);
+                        ldb_raw<CH>(c.gates + gate_off(tau, b, 2 * H + uc, B, 4 * H), wn, false);
+                        ldb_raw<CH>(c.gates + gate_off(tau, b, 3 * H + uc, B, 4 * H), wg, false);
                         ldb_raw<CH>(c.hsx + (row + (c.reverse ? B : 0)) * H + uc, wh, false);   // the state before step s
                         if (c.dhs) {
                             if (c.dhs_f32) ldf<CH>(reinterpret_cast<const float*>(c.dhs) + row * H + uc, din);
@@ -292,7 +321,8 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
 // K = H.  BWD = true: N = U, K = 3H (A = gate gradients of the following step, pitch 4H).
 // =====================================================================================================
 template <int U, int NBT, bool BWD, int KCH>
-__global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
+__global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
+    constexpr int EW = Roles<U, NBT, BWD>::kEpi;
     constexpr int N = BWD ? U : 3 * U;
     constexpr uint32_t kAccCols = NBT * N;                     // accumulators; forward: + NBT*N projection columns
     constexpr uint32_t kNeedCols = BWD ? kAccCols : 2 * kAccCols;
@@ -322,20 +352,22 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         tc::prefetch_tmap(&c.tmW);
         tc::prefetch_tmap(&c.tmA);
         for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], 1); }
-        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], BWD ? kEpiWarps / NBT : kEpiWarps); }
+        for (int i = 0; i < NBT; ++i) { tc::mbar_init(&sm.acc_full[i], 1); tc::mbar_init(&sm.acc_empty[i], BWD ? EW / NBT : EW); }
         tc::mbar_init(sm.wbar, 1);
         for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(sm.tmem_slot, kTmemCols);
-    if (!BWD && warp >= kEpiWarp0 && warp < kEpiWarp0 + (int)kEpiWarps) {
-        for (int i = threadIdx.x - kEpiWarp0 * 32; i < 3 * U; i += kEpiThreads) sm.bias[i] = c.b_hh[(i / U) * H + u0 + (i % U)];
+    if (!BWD && warp >= kEpiWarp0 && warp < kEpiWarp0 + EW) {
+        for (int i = threadIdx.x - kEpiWarp0 * 32; i < 3 * U; i += EW * 32) sm.bias[i] = c.b_hh[(i / U) * H + u0 + (i % U)];
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
-    const int lrank = state_loader_rank(warp), trank = tail_loader_rank(warp);
+    constexpr bool kLean = Roles<U, NBT, BWD>::kLean;
+    const int lrank = state_loader_rank(warp, kEpiWarp0 + EW, kLean), trank = tail_loader_rank(warp, kEpiWarp0 + EW, kLean);
+    const int n_ls = kLean ? 1 : P.ls, n_lw = kLean ? 1 : P.lw;
 
     // iteration i: forward step s = i (A slab = s: the state before the step);
     // backward s = T-1-i for i = 0..T (s = -1 finishes dh0); the product of iteration i >= 1 reads slab s+1 of dg.
@@ -365,14 +397,14 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
             const int nst = nkc / KCH;                                            // stages per (step, batch tile)
             uint32_t st = 0, ph = 1;                                              // ph: parity that means "slot free"
             int turn = 0;                                                         // stages are dealt round-robin to the loaders
-            const int LS = P.ls;
+            const int LS = n_ls;
             for (int i = BWD ? 1 : 0; i < n_iters; ++i) {
                 // forward: the state before step s=i;  backward (s = T-1-i): the gate gradient of step s+1
                 const int slab = BWD ? (c.reverse ? i - 1 : T - i) : (c.reverse ? T - i : i);
                 for (int bt = 0; bt < NBT; ++bt) {
                     if (lrank == 0) FN_STAMP(i, bt, 0);
                     if (i > 0) {
-                        fn_spin_until(gbar + tile0 + bt, (unsigned)(P.nslices * i) * (BWD ? kEpiWarps / NBT : kEpiWarps));
+                        fn_spin_until(gbar + tile0 + bt, (unsigned)(P.nslices * i) * (unsigned)(BWD ? EW / NBT : EW));
                         if (lrank == 0) FN_STAMP(i, bt, 1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
@@ -470,7 +502,7 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         // ------------------------------- streamed part of the weight slice -----------------------------
         if (nstream > 0) {
             int turn = 0;
-            const int LW = P.lw;
+            const int LW = n_lw;
             const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
             const int n_tilesteps = T * NBT, nsst = nstream / KCH;           // streamed stages per (step, batch tile)
             const uint32_t slot_bytes = (uint32_t)(KCH * w_chunk_bytes);
@@ -502,10 +534,10 @@ __global__ void __launch_bounds__(kThreadsGru, 1) gru_tc_kernel(const __grid_con
         }
     };
 
-    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + (int)kEpiWarps) epilogue_role<U, NBT, BWD>(P, c, sm, tmem_base, gbar, u0, tile0, warp, lane);
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + EW) epilogue_role<U, NBT, BWD>(P, c, sm, tmem_base, gbar, u0, tile0, warp, lane);
     else if (warp == 1) mma_role();
-    else if (lrank >= 0 && lrank < P.ls) state_loader_role();
-    else if (trank >= 0 && trank < P.lw) tail_loader_role();
+    else if (lrank >= 0 && lrank < n_ls) state_loader_role();
+    else if (trank >= 0 && trank < n_lw) tail_loader_role();
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
@@ -537,7 +569,7 @@ int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(P.n_chains * P.tsplit * P.nslices);
-    cfg.blockDim = dim3(kThreadsGru);
+    cfg.blockDim = dim3(Roles<U, NBT, BWD>::kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];

@@ -20,6 +20,11 @@ from .ops import F32, ChainSpec, _f32c, _p, _st, col_sum, gemm
 BF16 = torch.bfloat16
 
 
+def _pad32(n: int) -> int:
+    """Rows of a saved-gates slab: the kernels store them in 32-row x 16-column blocks (include/fadernets_b200.h)."""
+    return (n + 31) // 32 * 32
+
+
 def r8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -250,7 +255,7 @@ class GruGroupBf16Fn(torch.autograd.Function):
             ch.reverse = 1 if sp.reverse else 0
             d["hsx"] = hsx
             if need_grad:
-                gates = torch.empty((T, B, 4 * H), dtype=BF16, device=dev)
+                gates = torch.empty((T, _pad32(B), 4 * H), dtype=BF16, device=dev)
                 ch.gates = gates.data_ptr()
                 d["gates"] = gates
             if sp.final is not None:
@@ -360,7 +365,7 @@ class DecoderStackBf16Fn(torch.autograd.Function):
             hsx = torch.empty((T + 1, B, H), dtype=BF16, device=dev)
             LIB.call("fn_cast_bf16", _p(h0), H, 1, _p(hsx), H, B, H, st)
             d["hsx"] = hsx
-            d["gates"] = torch.empty((T, B, H4), dtype=BF16, device=dev) if need_grad else None
+            d["gates"] = torch.empty((T, _pad32(B), H4), dtype=BF16, device=dev) if need_grad else None
             keep.append(d)
         w_ih2, b_ih2, w_hh2, b_hh2 = tensors[18:22]
         g = keep[2]
@@ -369,7 +374,7 @@ class DecoderStackBf16Fn(torch.autograd.Function):
         d2["w_hh_b"] = cast_bf16(w_hh2, K3, H, H, 1)
         d2["w_ih_b"] = cast_bf16(w_ih2, K3, H, H, 1)
         d2["hsx"] = torch.empty((T + 1, B, H), dtype=BF16, device=dev)
-        d2["gates"] = torch.empty((T, B, H4), dtype=BF16, device=dev) if need_grad else None
+        d2["gates"] = torch.empty((T, _pad32(B), H4), dtype=BF16, device=dev) if need_grad else None
         dense = torch.empty((T, B, K3), dtype=BF16, device=dev)
         keep.append(d2)
 
@@ -388,7 +393,7 @@ class DecoderStackBf16Fn(torch.autograd.Function):
                     ch.proj, ch.proj_ld = d["proj"].data_ptr(), K3
                     ch.hsx = d["hsx"].data_ptr() + t0 * B * H * 2
                     if need_grad:
-                        ch.gates = d["gates"].data_ptr() + t0 * B * H4 * 2
+                        ch.gates = d["gates"].data_ptr() + t0 * _pad32(B) * H4 * 2
             if k >= 1:
                 t0 = (k - 1) * L
                 # cell 2's input projection for this segment: dense[t] = hs_g[t] W_ih2^T + b_ih2, hs_g[t] = slab t+1
@@ -400,7 +405,7 @@ class DecoderStackBf16Fn(torch.autograd.Function):
                 ch.dense = dense.data_ptr() + t0 * B * K3 * 2
                 ch.hsx = d2["hsx"].data_ptr() + t0 * B * H * 2
                 if need_grad:
-                    ch.gates = d2["gates"].data_ptr() + t0 * B * H4 * 2
+                    ch.gates = d2["gates"].data_ptr() + t0 * _pad32(B) * H4 * 2
             LIB.call("fn_gru_seq_fwd_bf16", chains, n, B, L, H, _p(bar), bar.numel(), st)
         for d in keep:
             d.pop("emb", None); d.pop("proj", None)
@@ -434,7 +439,7 @@ class DecoderStackBf16Fn(torch.autograd.Function):
             t0 = j * L
             ch.w_hh_t = whts[ci].data_ptr()
             ch.hsx = d["hsx"].data_ptr() + t0 * B * H * 2
-            ch.gates = d["gates"].data_ptr() + t0 * B * H4 * 2
+            ch.gates = d["gates"].data_ptr() + t0 * _pad32(B) * H4 * 2
             ch.dg = dgs[ci].data_ptr() + t0 * B * H4 * 2
             if dhs[ci] is not None:
                 ch.dhs = dhs[ci].data_ptr() + t0 * B * H * dhs[ci].element_size()
