@@ -86,13 +86,23 @@ __device__ __forceinline__ void stf(float* p, const float (&v)[W]) {
     for (int i = 0; i < W / 4; ++i)
         *(reinterpret_cast<float4*>(p) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-// packed bf16: W/2 32-bit words
+// packed bf16: W/2 32-bit words.  W = 16 (32 bytes, 32-byte aligned) is ONE 256-bit access: the epilogues' rows are 8 KB
+// apart, so every lane of a load / store touches its own sector and the LSU cost is per instruction x sector.
 template <int W>
 __device__ __forceinline__ void ldb_raw(const __nv_bfloat16* p, uint32_t (&w)[W / 2], bool coherent) {
+    if constexpr (W == 16) {
+        if (coherent)
+            asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+        else
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+    } else {
 #pragma unroll
-    for (int i = 0; i < W / 8; ++i) {
-        const uint4 t = coherent ? __ldcg(reinterpret_cast<const uint4*>(p) + i) : __ldg(reinterpret_cast<const uint4*>(p) + i);
-        w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        for (int i = 0; i < W / 8; ++i) {
+            const uint4 t = coherent ? __ldcg(reinterpret_cast<const uint4*>(p) + i) : __ldg(reinterpret_cast<const uint4*>(p) + i);
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
     }
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -110,9 +120,14 @@ __device__ __forceinline__ void stb(__nv_bfloat16* p, const float (&v)[W]) {
         const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
         w[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
+    if constexpr (W == 16) {
+        asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    } else {
 #pragma unroll
-    for (int i = 0; i < W / 8; ++i)
-        __stcg(reinterpret_cast<uint4*>(p) + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+        for (int i = 0; i < W / 8; ++i)
+            __stcg(reinterpret_cast<uint4*>(p) + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+    }
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
