@@ -74,6 +74,17 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ---- W-wide vector loads / stores (W = 8 or 16 elements, 16-byte aligned) ----------------------------
 template <int W>
 __device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[W]) {      // read-only fp32
+    if constexpr (W % 8 == 0) {
+        if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {                              // 256-bit accesses (see ldb_raw)
+#pragma unroll
+            for (int i = 0; i < W / 8; ++i)
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(v[8 * i]), "=f"(v[8 * i + 1]), "=f"(v[8 * i + 2]), "=f"(v[8 * i + 3]), "=f"(v[8 * i + 4]),
+                               "=f"(v[8 * i + 5]), "=f"(v[8 * i + 6]), "=f"(v[8 * i + 7])
+                             : "l"(p + 8 * i));
+            return;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < W / 4; ++i) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
