@@ -44,12 +44,34 @@ struct TcChain {
 // A single issuing warp sustains only ~30 B/clk of TMA ingest on B200 (tools/ubench_tc.cu: 30 / 73 / 110 / 126 B/clk
 // per SM with 1 / 2 / 3 / 4 issuing warps), so the ring stages are dealt round-robin to several loader warps.
 // (setmaxnreg re-balancing between warpgroups was tried: ptxas then spills in the 80-register control roles.)
+#ifndef FN_EPI16
+#define FN_EPI16 0      /* 1: sixteen epilogue warps in the tile-split BPTT (measured slower once the epilogue accesses were coalesced: 18.6 vs 17.3 ms) */
+#endif
+#ifndef FN_PUB_CTA
+#define FN_PUB_CTA 0     /* measured neutral (forward 11.6 vs 11.4 ms), off.  1: ONE release per (CTA, tile, step) after a named barrier of the tile's epilogue warps; 0: one per warp */
+#endif
 constexpr int kEpiWarp0 = 4;
+// Publish a finished (step, tile) of this CTA to the other slices of the chain.  `nthr` epilogue threads work on the tile
+// (barrier `id`); their stores happen-before the barrier, the barrier before the elected thread's release (cumulative at
+// gpu scope), so ONE red.release per CTA is enough -- 8-16x fewer atomics on the step counter the consumers poll.
+__device__ __forceinline__ void publish_tile(unsigned* ctr, int id, int nthr, bool leader) {
+#if FN_PUB_CTA
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory");
+    if (leader) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        fn_red_release(ctr, 1u);
+    }
+#else
+    publish(ctr);
+#endif
+}
+template <int EW, int NBT, bool BWD>
+__host__ __device__ constexpr unsigned publishes_per_step() { return FN_PUB_CTA ? 1u : (unsigned)(BWD ? EW / NBT : EW); }
 // Epilogue warps of an instantiation: 8, or 16 for the tile-split BPTT (64-unit slices, one batch tile per CTA): there a
 // thread then owns ONE 16-unit chunk of its row and fetches all of its saved gates before the accumulator is ready; with
 // 8 warps the second chunk's loads sat on the step's critical path (gate-gradient epilogue 8.4k of the 30k-cycle step).
 template <int U, int NBT, bool BWD> struct Roles {
-    static constexpr int kEpi = (BWD && U == 64 && NBT == 1) ? 16 : 8;       // epilogue warps 4 .. 4 + kEpi - 1
+    static constexpr int kEpi = (BWD && U == 64 && NBT == 1 && FN_EPI16) ? 16 : 8;       // epilogue warps 4 .. 4 + kEpi - 1
     // 8 epilogue warps: + state loader 3 and tail loaders 0-1 after them (15 warps, 128 registers per thread).
     // 16 epilogue warps: no optional loaders, the tail loader is warp 2 (20 warps, 96 registers per thread).
     static constexpr bool kLean = kEpi == 16;
@@ -187,7 +209,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     }
                     if (row_ok) stb<UT>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hreg[bt]);
                     if (stamp) FN_STAMP(s, bt, 9);
-                    if (s + 1 < T) publish(gbar + tile0 + bt);               // the next step only needs the state
+                    if (s + 1 < T) publish_tile(gbar + tile0 + bt, 1, EW * 32, warp == kEpiWarp0 && lane == 0);   // the next step only needs the state
                     if (stamp) FN_STAMP(s, bt, 10);
                     if (row_ok) {
                         if (c.gates) {                               // off the critical path: after the publish
@@ -307,7 +329,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                 }
                 if (s < 0) continue;
                 if (stamp) FN_STAMP(i, bt, 9);
-                publish(gflag);                              // the recurrence consumes (dr, dz, dn*r) only
+                publish_tile(gflag, NBT == 2 ? 1 + grp : 1, NBT == 2 ? 128 : EW * 32, (NBT == 2 ? (warp - kEpiWarp0) % 4 == 0 : warp == kEpiWarp0) && lane == 0);   // the recurrence consumes (dr, dz, dn*r) only
                 if (stamp) FN_STAMP(i, bt, 10);
                 if (NCHK == 1 && row_ok) stb<CH>(c.dg + row * 4 * H + u0 + uu0 + 2 * H, o_i);
             }
@@ -404,7 +426,7 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
                 for (int bt = 0; bt < NBT; ++bt) {
                     if (lrank == 0) FN_STAMP(i, bt, 0);
                     if (i > 0) {
-                        fn_spin_until(gbar + tile0 + bt, (unsigned)(P.nslices * i) * (unsigned)(BWD ? EW / NBT : EW));
+                        fn_spin_until(gbar + tile0 + bt, (unsigned)(P.nslices * i) * publishes_per_step<EW, NBT, BWD>());
                         if (lrank == 0) FN_STAMP(i, bt, 1);
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
