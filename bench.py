@@ -18,9 +18,12 @@ import sys
 # stdout carries exactly ONE JSON line.  Libraries write banners to the C-level stdout (NCCL / c10d print
 # "NCCL version ..." when the first communicator is created), so file descriptor 1 is pointed at stderr for the whole
 # run and the JSON line goes to a private duplicate of the original stdout.
-sys.stdout.flush()
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+if __name__ == "__main__":
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+else:                                   # imported: leave the importer's stdout alone
+    _JSON_OUT = sys.stdout
 
 
 def emit(line: dict) -> None:
