@@ -41,8 +41,9 @@ struct TcChain {
 
 // Warp roles (15 warps; 23 in the tile-split BPTT, see Roles): warp 0 = state loader 0 (+ resident weights), warp 1 = MMA issuer, warps 2-3 = state loaders 1-2,
 // warps 4-11 = the 8 gate-epilogue warps, warp 12 = state loader 3, warps 13-14 = weight-tail loaders 0-1.
-// A single issuing warp sustains only ~30 B/clk of TMA ingest on B200 (tools/ubench_tc.cu: 30 / 73 / 110 / 126 B/clk
-// per SM with 1 / 2 / 3 / 4 issuing warps), so the ring stages are dealt round-robin to several loader warps.
+// tools/ubench_tc.cu gets 30 / 73 / 110 / 126 B/clk of TMA ingest per SM with 1 / 2 / 3 / 4 issuing warps, so the ring
+// stages CAN be dealt round-robin to several loader warps (FN_GRU_LS / FN_GRU_LW); in this kernel it was measured
+// neutral (one loader thread sustains ~56 B/clk here and the MMA warp / the step chain pace it): one loader each.
 // (setmaxnreg re-balancing between warpgroups was tried: ptxas then spills in the 80-register control roles.)
 #ifndef FN_EPI16
 #define FN_EPI16 0      /* 1: sixteen epilogue warps in the tile-split BPTT (measured slower once the epilogue accesses were coalesced: 18.6 vs 17.3 ms) */

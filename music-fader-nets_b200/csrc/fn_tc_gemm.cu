@@ -65,9 +65,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t st = 0, ph = 1;
         for (int kb = 0; kb < nkb; ++kb) {
             tc::mbar_wait_u32(empty0 + st * 8u, ph);                   // slot free (passes immediately on first lap)
-            // A stage is 4 boxes of 64 rows x 64 columns (8 KB): lanes 0..3 issue one each.  One issuing thread
-            // sustains only one TMA op per ~450 cycles on B200 (tools/ubench_tc.cu), whatever the box size; several
-            // lanes of one converged instruction scale almost linearly (8 boxes of 32 rows measured slower than 4 of 64).
+            // A stage is 4 boxes of 64 rows x 64 columns (8 KB): lanes 0..3 issue one each.  In tools/ubench_tc.cu one
+            // issuing thread completes a TMA op per ~450 cycles whatever the box size while several lanes of one
+            // converged instruction scale almost linearly; here it is worth +10-14 % (FN_GEMM_LANES=1 is the old way,
+            // 8 boxes of 32 rows measured slower than 4 of 64).
             if (lane == 0) tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, kStageBytes);
             for (int op = lane; op < 4; op += p.issue_lanes) {
                 if (lane >= p.issue_lanes) break;
