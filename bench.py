@@ -124,12 +124,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synth_host_batch(B, T, seed):
-    from oracle import fader_oracle as fo          # only for the synthetic-data recipe shared with the tests
-    d, r, n, c, rd, nd = fo.synth_batch(B, T, seed=seed)
-    return d, r, n, c, rd, nd
-
-
 def make_batch_pinned(B, T, seed):
     """Synthetic event-token batch in PINNED host memory, in the dataset's tuple layout."""
     g = torch.Generator().manual_seed(seed)
@@ -265,11 +259,9 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(sec / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": prec, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: Music{'AttrRegGMVAE' if variant == 'gmvae' else 'AttrRegVAE'} "
-                               f"train step, batch {B}/GPU x seq_len {T}, hidden {H}, z {Z}, K {K}, {prec}",
-                   "global_batch": gbatch, "seq_len": T, "hidden": H, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (saved gates + states, > 1 GB) exceeds the 126 MB L2; no flush needed",
-                   "weights": "torch default init, manual_seed(0)", "step": STEP0},
+        "config": dict(workload_config(args.workload, world),
+                       l2="per-step working set (saved gates + states, > 1 GB) exceeds the 126 MB L2; no flush needed",
+                       weights="torch default init, manual_seed(0)", step=STEP0),
         "e2e": {"value": round(e2e, 2), "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": round(sec_e2e / args.steps * 1e3, 3)},
         "gpu_launches": launches,
@@ -290,7 +282,22 @@ def run_ours(args):
     if breakdown:
         line["breakdown_ms_per_step"] = breakdown       # C-ABI call -> [ms per step, calls per step] (event-timed, serial)
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_reference(args.workload, steps=1, warmup=1)
+        line["cpu_baseline"] = cpu_reference(args.workload, steps=3, warmup=1, budget_s=25.0)
+    if not args.no_gpu_reference and world == 1:
+        # the bar to beat: the reference's own GPU path -- cuDNN GRU, cuBLAS, ATen through torch -- on this B200
+        from baseline import ref_runner
+        why = ref_runner.available()
+        if why is None:
+            del model, opt
+            torch.cuda.empty_cache()
+            sampler = ClockSampler(local).start()
+            gr = ref_runner.gpu_reference(variant, B, T, H, Z, K, steps=2, warmup=1)
+            gr["clocks"] = sampler.stop()
+            best = max((v.get("sequences_per_s", 0.0) for v in gr.values() if isinstance(v, dict)), default=0.0)
+            gr["repo_e2e_over_reference_gpu"] = round(e2e / best, 2) if best else None
+            line["gpu_reference"] = gr
+        else:
+            line["gpu_reference"] = {"unavailable": why}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -369,47 +376,70 @@ def run_decode(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(workload, steps, warmup, sample_batch=None):
-    """The reference algorithm on the host cores: the oracle port (oracle/fader_oracle.py, dense one-hot
-    GEMMs like the reference's nn.GRU on one-hot input) on a BOUNDED sample of the workload."""
-    from oracle import fader_oracle as fo
+SAMPLE_BATCH = {"c1": 4, "c2": 8, "c2_bf16": 8, "c3": 4, "c3_f32": 4}     # the batch at which the CPU reference is fastest per sequence
+
+
+def workload_config(workload, world):
+    """`config` of the JSON line -- shared by the repo arm and the reference arm so that they describe the same workload."""
+    variant, B, T, H, Z, K, prec = WORKLOADS[workload]
+    return {"workload": f"{workload}: Music{'AttrRegGMVAE' if variant == 'gmvae' else 'AttrRegVAE'} "
+                        f"train step, batch {B}/GPU x seq_len {T}, hidden {H}, z {Z}, K {K}, {prec}",
+            "global_batch": B * world, "seq_len": T, "hidden": H, "parallelism": f"dp{world}"}
+
+
+def cpu_reference(workload, steps, warmup, budget_s=None):
+    """The reference's own CPU implementation on the host cores: the UNMODIFIED reference classes and its own
+    train() (baseline/_ref, see baseline/ref_runner.py) on a BOUNDED sample of the workload (reduced batch, same
+    seq_len / hidden; CPU sequences/s is ~flat in batch).  Falls back to the oracle port
+    (kind "port") only if baseline/_ref was not vendored."""
     variant, B, T, H, Z, K, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = sample_batch or {"c1": 4, "c2": 8, "c2_bf16": 8, "c3": 4, "c3_f32": 4}[workload]      # the batch at which the CPU port is fastest per sequence
-    w = fo.init_weights(H, Z, variant, max(K, 1), seed=0)
-    st = fo.AdamState(w)
-    batch = fo.synth_batch(Bs, T, seed=0)
-    g = torch.Generator().manual_seed(1)
-    times = []
-    for it in range(warmup + steps):
-        er, en = torch.randn(Bs, Z, generator=g), torch.randn(Bs, Z, generator=g)
-        t0 = time.perf_counter()
-        fo.train_step(w, st, variant, batch, er, en, STEP0, 0.2, 1e-3, dense_onehot=True)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    sec = float(np.mean(times))
-    return {"value": round(Bs / sec, 4), "unit": "sequences/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train step(s) of batch {Bs} (of {B}) x seq_len {T}, hidden {H}; {sec:.2f} s/step; "
-                      "CPU seq/s is ~flat in batch (BASELINE.md)", "ms_per_step": round(sec * 1e3, 1)}
+    Bs = SAMPLE_BATCH[workload]
+    from baseline import ref_runner
+    why = ref_runner.available()
+    if why is None:
+        sec, done, last = ref_runner.time_train(variant, Bs, T, H, Z, K, "cpu", steps, warmup, budget_s=budget_s)
+        kind = "reference"
+    else:
+        from oracle import fader_oracle as fo
+        w = fo.init_weights(H, Z, variant, max(K, 1), seed=0)
+        st = fo.AdamState(w)
+        batch = fo.synth_batch(Bs, T, seed=0)
+        g = torch.Generator().manual_seed(1)
+        times = []
+        for it in range(warmup + steps):
+            er, en = torch.randn(Bs, Z, generator=g), torch.randn(Bs, Z, generator=g)
+            t0 = time.perf_counter()
+            fo.train_step(w, st, variant, batch, er, en, STEP0, 0.2, 1e-3, dense_onehot=True)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        sec, done, kind = float(np.mean(times)), steps, "port"
+    return {"value": round(Bs / sec, 4), "unit": "sequences/s", "cores": cores, "kind": kind,
+            "sample": f"{done} timed + {warmup} warm-up train step(s) of batch {Bs} (of {B}) x seq_len {T}, hidden {H}, fp32; "
+                      f"{sec:.2f} s/step; CPU sequences/s is ~flat in batch (BASELINE.md)"
+                      + ("" if why is None else f"; oracle port because {why}"),
+            "sample_batch": Bs, "steps": done, "warmup": warmup, "ms_per_step": round(sec * 1e3, 1)}
 
 
 def run_reference(args):
+    """--impl reference: the unmodified reference's CPU train step on all host cores.  Exactly `--warmup` + `--steps`
+    steps run; one step = one train() call on a bounded sample (SAMPLE_BATCH sequences of the workload's seq_len /
+    hidden), so value = sample_batch / seconds per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     variant, B, T, H, Z, K, prec = WORKLOADS[args.workload]
-    cb = cpu_reference(args.workload, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup else 0)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cb = cpu_reference(args.workload, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    cfg = workload_config(args.workload, world)
+    cfg.update({"sample_batch": cb["sample_batch"],
+                "note": "unmodified reference classes + train() (fp32, nn.GRU on dense one-hots) on the host cores; each step = "
+                        "one train() on a bounded sample of the workload (sample_batch sequences, same seq_len / hidden)"})
     line = {"impl": "reference", "metric": "sequences/sec GM-VAE train step", "value": cb["value"],
-            "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "unit": "sequences/s", "n_gpus": world, "steps": cb["steps"], "warmup": cb["warmup"],
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: Music{'AttrRegGMVAE' if variant == 'gmvae' else 'AttrRegVAE'} "
-                                   f"train step, batch {B}/GPU x seq_len {T}, hidden {H}, z {Z}, K {K}, {prec}",
-                       "global_batch": B * world, "seq_len": T, "hidden": H, "parallelism": f"dp{world}",
-                       "note": "reference algorithm (fp32, dense one-hot GEMMs) on the host cores; bounded sample, see cpu_baseline.sample"},
-            "cpu_baseline": cb,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -424,6 +454,7 @@ def main():
                          "c2 = configs[1] (fp32 exact-parity path); c1 = configs[0]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the unmodified reference on this GPU")
     ap.add_argument("--breakdown", action="store_true", help="add per-C-ABI-call device time to the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
