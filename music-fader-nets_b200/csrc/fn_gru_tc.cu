@@ -25,6 +25,7 @@
 // "the state before step s" is slab tau (forward) / tau+1 (reverse) and lines up row for row with
 // gates[tau] / dg[tau] in the batched weight-gradient GEMMs.
 #include "fn_gru_tc_common.cuh"
+#include "fn_gru_tc2.h"
 
 namespace {
 
@@ -109,10 +110,6 @@ struct TcLaunch {
 // (1 KB; block order: time slab, 32-row block, 16-column block) instead of [T][B][4H] rows: a warp of the epilogue owns
 // 32 consecutive rows x 16 (or 8) consecutive units, i.e. exactly one block per gate, so its loads and stores are
 // contiguous 512-1024 B instead of 32 sectors 8 KB apart (the epilogues are LSU-transaction bound).
-__device__ __forceinline__ long long gate_off(long long t, int b, int col, int B, int H4) {
-    const long long row_blocks = (B + 31) >> 5;
-    return ((t * row_blocks + (b >> 5)) * (long long)(H4 >> 4) + (col >> 4)) * 512 + (b & 31) * 16 + (col & 15);
-}
 
 template <int U, int NBT, bool BWD>
 __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& c, const Smem& sm, const uint32_t tmem_base, unsigned* gbar,
@@ -717,6 +714,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
 
 // Profiling aid: when set (device buffer of >= (T+1)*2*64 int64), CTA 0 of every following launch records
 // clock64 stamps of its pipeline events (see FN_STAMP).  NULL switches it off.  Not part of the product path.
+long long* fn_gru_dbg_ptr() { return g_dbg; }
 extern "C" int fn_gru_debug_timeline(void* device_buffer) {
     g_dbg = reinterpret_cast<long long*>(device_buffer);
     return FN_OK;
@@ -724,9 +722,13 @@ extern "C" int fn_gru_debug_timeline(void* device_buffer) {
 
 extern "C" int fn_gru_seq_fwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
                                    size_t barrier_ws_bytes, void* stream) {
+    if (fn_gru2_eligible(false, n_chains, B, H))          // two batch tiles: the CTA-pair kernel (fn_gru_tc2.cu)
+        return fn_gru2_run(false, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
     return run_tc(false, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
 }
 extern "C" int fn_gru_seq_bwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
                                    size_t barrier_ws_bytes, void* stream) {
+    if (fn_gru2_eligible(true, n_chains, B, H))
+        return fn_gru2_run(true, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
     return run_tc(true, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
 }

@@ -47,6 +47,36 @@ __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two loads, ONE wait (accumulator + time-invariant columns of a gate)
+template <int W>
+__device__ __forceinline__ void tmem_ld2(uint32_t ta, float (&a)[W], uint32_t tb, float (&b)[W]) {
+    uint32_t ra[W], rb[W];
+    if constexpr (W == 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(ra[0]), "=r"(ra[1]), "=r"(ra[2]), "=r"(ra[3]), "=r"(ra[4]), "=r"(ra[5]), "=r"(ra[6]), "=r"(ra[7]), "=r"(ra[8]),
+              "=r"(ra[9]), "=r"(ra[10]), "=r"(ra[11]), "=r"(ra[12]), "=r"(ra[13]), "=r"(ra[14]), "=r"(ra[15])
+            : "r"(ta) : "memory");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rb[0]), "=r"(rb[1]), "=r"(rb[2]), "=r"(rb[3]), "=r"(rb[4]), "=r"(rb[5]), "=r"(rb[6]), "=r"(rb[7]), "=r"(rb[8]),
+              "=r"(rb[9]), "=r"(rb[10]), "=r"(rb[11]), "=r"(rb[12]), "=r"(rb[13]), "=r"(rb[14]), "=r"(rb[15])
+            : "r"(tb) : "memory");
+    } else {
+        static_assert(W == 8, "tmem_ld2: 8 or 16 columns");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(ra[0]), "=r"(ra[1]), "=r"(ra[2]), "=r"(ra[3]), "=r"(ra[4]), "=r"(ra[5]), "=r"(ra[6]), "=r"(ra[7])
+                     : "r"(ta) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(rb[0]), "=r"(rb[1]), "=r"(rb[2]), "=r"(rb[3]), "=r"(rb[4]), "=r"(rb[5]), "=r"(rb[6]), "=r"(rb[7])
+                     : "r"(tb) : "memory");
+    }
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < W; ++i) { a[i] = __uint_as_float(ra[i]); b[i] = __uint_as_float(rb[i]); }
+}
 template <int W>
 __device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[W]);
 template <>
@@ -139,6 +169,15 @@ __device__ __forceinline__ void stb(__nv_bfloat16* p, const float (&v)[W]) {
         for (int i = 0; i < W / 8; ++i)
             __stcg(reinterpret_cast<uint4*>(p) + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
     }
+}
+
+// The saved gates are private to the forward / backward kernels, so they are stored in [32 rows][16 columns] blocks
+// (1 KB; block order: time slab, 32-row block, 16-column block) instead of [T][B][4H] rows: a warp of the epilogue owns
+// 32 consecutive rows x 16 (or 8) consecutive units, i.e. exactly one block per gate, so its loads and stores are
+// contiguous 512-1024 B instead of 32 sectors 8 KB apart (the epilogues are LSU-transaction bound).
+__device__ __forceinline__ long long gate_off(long long t, int b, int col, int B, int H4) {
+    const long long row_blocks = (B + 31) >> 5;
+    return ((t * row_blocks + (b >> 5)) * (long long)(H4 >> 4) + (col >> 4)) * 512 + (b & 31) * 16 + (col & 15);
 }
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
