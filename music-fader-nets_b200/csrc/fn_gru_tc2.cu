@@ -27,8 +27,6 @@ namespace {
 constexpr int kEpi0 = 4;                       // warps 0-3: state loader, MMA issuer (+ TMEM), weight loader, store + publish
 constexpr int kEW2 = 16;                       // epilogue warps
 constexpr int kThreads2 = (kEpi0 + kEW2) * 32; // 640
-constexpr int kUP = 64;                        // hidden units per CTA pair
-constexpr int kStg = 128 * kUP * 2;            // staging tile of the new state: 128 rows x 64 units bf16 = 16 KB
 
 struct Tc2Chain {
     CUtensorMap tmW;       // fwd: W_hh [3H][H] as (k64, unit, gate, kchunk), box (64, 32, 3, KCH);  bwd: W_hh^T [H][3H] as (k64, unit, kchunk), box (64, 32, KCH)
@@ -45,25 +43,25 @@ struct Tc2Launch {
     Tc2Chain c[kMaxChainsTc];
     unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
     long long* dbg;        // profiling aid (fn_gru_debug_timeline): [step][64] clock64 stamps of CTA 0, or NULL
-    int n_chains, npairs, B, T, H;
+    int n_chains, ppc, cpp, B, T, H;   // ppc: pairs per chain (H / 32); cpp: chains per pair (1 or 2)
     int stages, kres, wst; // state-ring stages (of KCH chunks); resident weight chunks; weight-ring slots (of KCH chunks)
 };
 
 struct Smem2 {
     uint8_t *W, *WR, *A, *stg;
-    uint64_t *full, *empty, *wfull, *wempty, *wbar, *acc_full;
+    uint64_t *full, *empty, *wfull, *wempty, *wbar, *acc_full;    // acc_full: one per chain of the pair
     uint32_t* tmem_slot;
     float* bias;
 };
-constexpr size_t kSmemTail2 = 1024 /*align*/ + 1024 /*barriers + tmem slot*/ + 3 * kUP * 4 /*bias*/;
-__device__ __forceinline__ Smem2 carve2(uint8_t* raw, int w_res_bytes, int w_ring_bytes, int a_ring_bytes) {
+constexpr size_t kSmemTail2 = 1024 /*align*/ + 1024 /*barriers + tmem slot*/ + 1024 /*bias*/;
+__device__ __forceinline__ Smem2 carve2(uint8_t* raw, int w_res_bytes, int w_ring_bytes, int a_ring_bytes, int stg_bytes) {
     Smem2 s;
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     s.W = base; s.WR = s.W + w_res_bytes; s.A = s.WR + w_ring_bytes; s.stg = s.A + a_ring_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s.stg + kStg);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s.stg + stg_bytes);
     s.full = bars; s.empty = s.full + kMaxStages; s.wfull = s.empty + kMaxStages; s.wempty = s.wfull + kMaxWst;
     s.wbar = s.wempty + kMaxWst; s.acc_full = s.wbar + 1;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.acc_full + 1);
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.acc_full + 2);
     s.bias = reinterpret_cast<float*>(bars + 128);
     return s;
 }
@@ -105,41 +103,72 @@ __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 
     } while (0)                   // named barrier: epilogue warps (arrive) -> store warp (sync)
 
 // =====================================================================================================
-// Forward.  Accumulator columns of a CTA (its 128 rows x the pair's 192 gate columns):
-//   [ r z n of units 0..31 (the B half held by CTA 0) | r z n of units 32..63 (held by CTA 1) ], 32 columns each;
-// columns [192, 384) hold the time-invariant part of the pre-activations in the same order.
+// Forward.  Geometry: a pair owns kUP = 32 units of a chain (MMA N = 96: r, z, n), CTA r of the pair holds the
+// 3 x 16 weight rows of units [u0 + 16 r, +16) (6 KB per 64-wide K chunk) and batch tile r.  A pair serves ONE or TWO
+// chains ("chains per pair", cpp): with two, the chains are independent recurrences that take turns on the tensor
+// cores -- while chain A's gate epilogue, TMA store, hand-over and the first loads of its next step run (the part of a
+// step that is pure latency), the pair multiplies chain B.  Accumulator columns of chain k: [k*96, +96) =
+// [ r z n of the leader's 16 units | r z n of the peer's 16 units ]; columns 192 + the same hold the time-invariant
+// part of the pre-activations.
 // =====================================================================================================
-template <int KCH>
+// Two geometries (template parameter UP = units of a chain per pair): UP = 32 with up to two chains per pair (above), and
+// UP = 64 with one chain per pair (N = 192: half the state bytes per FLOP, for launches whose chains each get H/64 pairs).
+template <int UP> struct Geo {
+    static constexpr int kN = 3 * UP, kNW = kN / 2, kWCh = kNW * 128, kUT = UP / 4;
+    static constexpr int kStg = 128 * UP * 2;                  // staging tile of a chain's new state: 128 rows x UP units bf16
+    static constexpr int kMaxCpp = 64 / UP;
+};
+constexpr int kStgAll = 16384;                                 // staging bytes of a CTA (both geometries)
+constexpr int kAccCols = 192;                                  // accumulator columns of a CTA (both geometries); projections follow
+
+// swizzled (64B) byte offset of the 16-byte chunk `k16` (0..3) of row `row` in a [rows][64 B] tile (TMA SWIZZLE_64B)
+__device__ __forceinline__ uint32_t swz64(int row, int k16) { return (uint32_t)(row * 64 + ((k16 ^ ((row >> 1) & 3)) << 4)); }
+
+// sigmoid of two pre-activations with ONE SFU instruction (tanh.approx.f16x2): the gate epilogue is bound by the SFU
+// (3 transcendentals per unit and row); r and z are stored in bf16 (2^-9) and tolerate the f16 evaluation (2^-11).
+__device__ __forceinline__ void sigmoid2(float x0, float x1, float& y0, float& y1) {
+    uint32_t h, t;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(0.5f * x1), "f"(0.5f * x0));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+    asm("fma.rn.f16x2 %0, %1, %2, %2;" : "=r"(h) : "r"(t), "r"(0x38003800u));      // 0.5 t + 0.5
+    asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(y0), "=f"(y1) : "r"(h));
+}
+
+template <int UP, int KCH>
 __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_constant__ Tc2Launch P) {
-    constexpr int N = 3 * kUP;                                 // 192
-    constexpr int kWChunk = (N / 2) * 128;                     // 12 KB: one 64-wide K chunk of this CTA's half of the slice
+    constexpr int kUP = UP, kN = Geo<UP>::kN, kNW = Geo<UP>::kNW, kWCh = Geo<UP>::kWCh, kUT = Geo<UP>::kUT, kStgF = Geo<UP>::kStg;
+    constexpr int kMaxCpp = Geo<UP>::kMaxCpp;
     constexpr uint32_t kTmemCols = 512;                        // 192 accumulator + 192 projection columns
-    constexpr uint32_t a_stage = KCH * kATile, w_slot = KCH * kWChunk;
+    constexpr uint32_t a_stage = KCH * kATile, w_slot = KCH * kWCh;
     extern __shared__ uint8_t smem_raw[];
-    const int H = P.H, B = P.B, T = P.T, S = P.stages, WST = P.wst, kres = P.kres;
-    const int nkc = H / 64, nst = nkc / KCH, nsst = (nkc - kres) / KCH;          // stages per step; the streamed-weight ones come first
-    const Smem2 sm = carve2(smem_raw, kres * kWChunk, WST * (int)w_slot, S * (int)a_stage);
+    const int H = P.H, B = P.B, T = P.T, S = P.stages, WST = P.wst, kres = P.kres, cpp = P.cpp;
+    const int nkc = H / 64, nst = nkc / KCH, nsst = (nkc - kres) / KCH;          // stages per chain step; the streamed-weight ones come first
+    const Smem2 sm = carve2(smem_raw, cpp * kres * kWCh, WST * (int)w_slot, S * (int)a_stage, kStgAll);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = tc::cluster_ctarank();               // 0 = leader (issues the MMAs), owns batch tile `rank`
+    const uint32_t rank = tc::cluster_ctarank();               // 0 = leader (issues the MMAs); this CTA owns batch tile `rank`
     const int pair = blockIdx.x >> 1;
-    const int chain = pair / P.npairs, slice = pair % P.npairs;
-    const Tc2Chain& c = P.c[chain];
-    unsigned* gflag = P.bar + chain * 16 + rank;               // publishes of this CTA's batch tile
-    const int u0 = slice * kUP;                                // first unit of the pair
+    const int group = pair / P.ppc, slice = pair % P.ppc;
+    const int ch0 = group * cpp;                               // first chain of this pair
+    const int nact = P.n_chains - ch0 < cpp ? P.n_chains - ch0 : cpp;
+    const int u0 = slice * kUP;                                // first unit of the pair (in every chain it serves)
     const int b0 = (int)rank * 128;                            // first row of this CTA's batch tile
     const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;
 
     if (warp == 0 && lane == 0) {
-        tc::prefetch_tmap(&c.tmW); tc::prefetch_tmap(&c.tmA); tc::prefetch_tmap(&c.tmS);
+        for (int k = 0; k < nact; ++k) { tc::prefetch_tmap(&P.c[ch0 + k].tmW); tc::prefetch_tmap(&P.c[ch0 + k].tmA); tc::prefetch_tmap(&P.c[ch0 + k].tmS); }
         for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], 1); }
         for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
-        tc::mbar_init(sm.wbar, 1); tc::mbar_init(sm.acc_full, 1);
+        tc::mbar_init(sm.wbar, 1);
+        for (int k = 0; k < kMaxCpp; ++k) tc::mbar_init(&sm.acc_full[k], 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc_2cta(sm.tmem_slot, kTmemCols);
     if (warp >= kEpi0) {
-        for (int i = threadIdx.x - kEpi0 * 32; i < 3 * kUP; i += kEW2 * 32) sm.bias[i] = c.b_hh[(i / kUP) * H + u0 + (i % kUP)];
+        for (int i = threadIdx.x - kEpi0 * 32; i < nact * 3 * kUP; i += kEW2 * 32) {
+            const int k = i / (3 * kUP), j = i % (3 * kUP);
+            sm.bias[i] = P.c[ch0 + k].b_hh[(j / kUP) * H + u0 + (j % kUP)];
+        }
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -149,246 +178,265 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
 
     if (warp == 0) {
         // ------------------------------- state loader (both CTAs: own batch tile) ------------------------------
-        // Every load of the pair completes on the LEADER's barrier, which expects the bytes of both CTAs.
-        const uint32_t full_l = tc::smem_u32(sm.full) & tc::kPeerBitMask, empty0 = tc::smem_u32(sm.empty);
-        const uint32_t full0 = tc::smem_u32(sm.full);
+        // Every load of the pair completes on the LEADER's barrier, which expects the bytes of both CTAs.  A stage is ONE
+        // box of 128 rows x KCH chunks: tools/ubench_pair.cu measures ~230 cycles + bytes / 140 B/clk per TMA operation of
+        // one issuing thread (16 / 32 / 64 KB boxes: 45 / 70 / 94 B/clk per CTA), and SMALLER boxes from several lanes
+        // are slower still (8 KB x 4 lanes: 50 B/clk) -- so the boxes are as big as the ring allows.
+        const uint32_t full0 = tc::smem_u32(sm.full), full_l = full0 & tc::kPeerBitMask, empty0 = tc::smem_u32(sm.empty);
         const uint32_t a0 = tc::smem_u32(sm.A);
-        if (kres > 0 && tc::elect_one()) {
-            if (rank == 0) tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(2 * kres * kWChunk));
+        if (kres > 0) {
+            if (rank == 0 && lane == 0) tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(2 * nact * kres * kWCh));
+            __syncwarp();
             const uint32_t wbar_l = tc::smem_u32(sm.wbar) & tc::kPeerBitMask;
-            for (int kc = 0; kc < kres; kc += KCH)
-                tc::tma_load_4d_2cta_u32(tc::smem_u32(sm.W) + kc * kWChunk, &c.tmW, wbar_l, 0, u0 + (int)rank * 32, 0, kc);
+            for (int i = lane; i < nact * (kres / KCH); i += 32) {
+                const int k = i / (kres / KCH), kc = (i % (kres / KCH)) * KCH;
+                tc::tma_load_4d_2cta_u32(tc::smem_u32(sm.W) + (uint32_t)((k * kres + kc) * kWCh), &P.c[ch0 + k].tmW, wbar_l, 0, u0 + (int)rank * (kUP / 2), 0, kc);
+            }
         }
         __syncwarp();
         uint32_t st = 0, ph = 1;
         for (int i = 0; i < T; ++i) {
-            const int slab = c.reverse ? T - i : i;            // the state before step i
-            FN_STAMP2(i, 0);
-            if (i > 0) {
-                fn_spin_until(gflag, (unsigned)(P.npairs * i));
+            for (int k = 0; k < nact; ++k) {
+                const Tc2Chain& c = P.c[ch0 + k];
+                const int slab = c.reverse ? T - i : i;        // the state before step i
+                FN_STAMP2(i, k * 32 + 0);
+                if (i > 0) {
+                    fn_spin_until(P.bar + (ch0 + k) * 16 + rank, (unsigned)(P.ppc * i));
 #if FN_GRU2_FENCES
-                asm volatile("fence.proxy.async.global;" ::: "memory");
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
-            }
-            FN_STAMP2(i, 1);
-            int kc = kres;                                     // K order: streamed-weight chunks [kres, nkc) first, then [0, kres)
-            for (int j = 0; j < nst; ++j) {
-                if (j == nsst) kc = 0;
-                tc::mbar_wait_u32(empty0 + st * 8u, ph);
-                if (tc::elect_one()) {
-                    if (rank == 0) tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, 2 * a_stage);
-                    tc::tma_load_4d_2cta_u32(a0 + st * a_stage, &c.tmA, full_l + st * 8u, 0, b0, kc, slab);
                 }
-                __syncwarp();
-                kc += KCH;
-                if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                FN_STAMP2(i, k * 32 + 1);
+                int kc = kres;                                 // K order: streamed-weight chunks [kres, nkc) first, then [0, kres)
+                for (int j = 0; j < nst; ++j) {
+                    if (j == nsst) kc = 0;
+                    tc::mbar_wait_u32(empty0 + st * 8u, ph);
+                    if (tc::elect_one()) {
+                        if (rank == 0) tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, 2 * a_stage);
+                        tc::tma_load_4d_2cta_u32(a0 + st * a_stage, &c.tmA, full_l + st * 8u, 0, b0, kc, slab);
+                    }
+                    __syncwarp();
+                    kc += KCH;
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                }
+                FN_STAMP2(i, k * 32 + 2);
             }
-            FN_STAMP2(i, 2);
         }
     } else if (warp == 1) {
         // ------------------------------- MMA issuer (leader only) -----------------------------------------------
         if (rank == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(256, N, 0, 0);
+            const uint32_t idesc = tc::make_idesc_bf16(256, kN, 0, 0);
             if (kres > 0) tc::mbar_wait(sm.wbar, 0);
             const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
-            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty), accf = tc::smem_u32(sm.acc_full);
+            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty), accf0 = tc::smem_u32(sm.acc_full);
             const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
             const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
             const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
             uint32_t st = 0, ph = 0, ws = 0, wph = 0;
-            auto issue = [&](uint64_t ad, uint64_t bd, bool first) {
+            auto issue = [&](uint32_t d_tmem, uint64_t ad, uint64_t bd, bool first) {
 #pragma unroll
                 for (int q = 0; q < KCH; ++q) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_f16_2cta(tmem_base, ad + (uint64_t)(q * (kATile >> 4) + 2 * k), bd + (uint64_t)(q * (kWChunk >> 4) + 2 * k), idesc,
-                                          (q | k) ? 1u : (first ? 0u : 1u));
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc::umma_f16_2cta(d_tmem, ad + (uint64_t)(q * (kATile >> 4) + 2 * kk), bd + (uint64_t)(q * (kWCh >> 4) + 2 * kk), idesc,
+                                          (q | kk) ? 1u : (first ? 0u : 1u));
                 }
             };
             for (int i = 0; i < T; ++i) {
-                // (the accumulator is free: every chunk of this step's state was published after both CTAs' epilogues
-                // had read the previous accumulator -- the step dependency itself orders the reuse)
-                for (int j = 0; j < nsst; ++j) {
-                    tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
-                    FN_STAMP2(i, 32 + j);
-                    tc::mbar_wait_u32(full0 + st * 8u, ph);
-                    tc::tc_fence_after();
-                    FN_STAMP2(i, 16 + j);
-                    if (tc::elect_one()) {
-                        issue(adesc0 + (uint64_t)(st * (a_stage >> 4)), wdesc0 + (uint64_t)(ws * (w_slot >> 4)), j == 0);
-                        tc::umma_commit_2cta_mc_u32(wempty0 + ws * 8u, 3);
-                        tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, 3);
-                        if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf, 3);
+                // (a chain's accumulator is free: every chunk of this step's state was published after both CTAs'
+                // epilogues had read the previous accumulator -- the step dependency itself orders the reuse)
+                for (int k = 0; k < nact; ++k) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(k * kN);
+                    for (int j = 0; j < nsst; ++j) {
+                        tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
+                        tc::mbar_wait_u32(full0 + st * 8u, ph);
+                        tc::tc_fence_after();
+                        if (j == 0) FN_STAMP2(i, k * 32 + 3);
+                        if (tc::elect_one()) {
+                            issue(d_tmem, adesc0 + (uint64_t)(st * (a_stage >> 4)), wdesc0 + (uint64_t)(ws * (w_slot >> 4)), j == 0);
+                            tc::umma_commit_2cta_mc_u32(wempty0 + ws * 8u, 3);
+                            tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, 3);
+                            if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf0 + k * 8u, 3);
+                        }
+                        __syncwarp();
+                        if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
-                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
-                }
-                uint64_t bd = bdesc0;
-                for (int j = nsst; j < nst; ++j) {
-                    tc::mbar_wait_u32(full0 + st * 8u, ph);
-                    tc::tc_fence_after();
-                    FN_STAMP2(i, 16 + j);
-                    if (tc::elect_one()) {
-                        issue(adesc0 + (uint64_t)(st * (a_stage >> 4)), bd, j == 0);
-                        tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, 3);
-                        if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf, 3);
+                    uint64_t bd = bdesc0 + (uint64_t)(k * kres * (kWCh >> 4));
+                    for (int j = nsst; j < nst; ++j) {
+                        tc::mbar_wait_u32(full0 + st * 8u, ph);
+                        tc::tc_fence_after();
+                        if (j == 0) FN_STAMP2(i, k * 32 + 3);
+                        if (tc::elect_one()) {
+                            issue(d_tmem, adesc0 + (uint64_t)(st * (a_stage >> 4)), bd, j == 0);
+                            tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, 3);
+                            if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf0 + k * 8u, 3);
+                        }
+                        __syncwarp();
+                        bd += (uint64_t)(w_slot >> 4);
+                        if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
-                    bd += (uint64_t)(w_slot >> 4);
-                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                    FN_STAMP2(i, k * 32 + 4);
                 }
-                FN_STAMP2(i, 4);
             }
         }
     } else if (warp == 2) {
-        // ------------------------------- streamed part of the weight half (both CTAs) ---------------------------
+        // ------------------------------- streamed part of the weight halves (both CTAs) -------------------------
         // Independent of the recurrence: runs ahead of the step barrier, up to the ring depth.
         if (nsst > 0) {
             const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
             const uint32_t wfull_l = wfull0 & tc::kPeerBitMask;
             uint32_t ws = 0, wph = 1;
             for (int i = 0; i < T; ++i) {
-                for (int j = 0; j < nsst; ++j) {
-                    tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
-                    if (tc::elect_one()) {
-                        if (rank == 0) tc::mbar_arrive_expect_tx_u32(wfull0 + ws * 8u, 2 * w_slot);
-                        tc::tma_load_4d_2cta_u32(wr0 + ws * w_slot, &c.tmW, wfull_l + ws * 8u, 0, u0 + (int)rank * 32, 0, kres + j * KCH);
+                for (int k = 0; k < nact; ++k) {
+                    const Tc2Chain& c = P.c[ch0 + k];
+                    for (int j = 0; j < nsst; ++j) {
+                        tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
+                        if (tc::elect_one()) {
+                            if (rank == 0) tc::mbar_arrive_expect_tx_u32(wfull0 + ws * 8u, 2 * w_slot);
+                            tc::tma_load_4d_2cta_u32(wr0 + ws * w_slot, &c.tmW, wfull_l + ws * 8u, 0, u0 + (int)rank * (kUP / 2), 0, kres + j * KCH);
+                        }
+                        __syncwarp();
+                        if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
                 }
             }
         }
     } else if (warp == 3) {
         // ------------------------------- store + publish ---------------------------------------------------------
-        const uint32_t stg = tc::smem_u32(sm.stg);
         for (int s = 0; s < T; ++s) {
-            const int tau = c.reverse ? T - 1 - s : s;
-            asm volatile("bar.sync %0, %1;" ::"n"(kBarStage), "n"((kEW2 + 1) * 32) : "memory");
-            long long t8 = 0, t9 = 0, t12 = 0, t10 = 0;
-            if (dbg_on) t8 = clk();
-            if (tc::elect_one()) {
-                tc::tma_store_3d_u32(&c.tmS, stg, u0, b0, c.reverse ? tau : tau + 1);
-                tc::bulk_commit_group();
-                tc::bulk_wait_group<0>();                      // the tile is in global memory (and the staging tile reusable)
-            }
-            __syncwarp();
-            if (dbg_on) t9 = clk();
-            if (tc::elect_one()) {
-                if (s + 1 < T) {
+            for (int k = 0; k < nact; ++k) {
+                const Tc2Chain& c = P.c[ch0 + k];
+                const int tau = c.reverse ? T - 1 - s : s;
+                asm volatile("bar.sync %0, %1;" ::"r"(kBarStage + k), "n"((kEW2 + 1) * 32) : "memory");
+                if (tc::elect_one()) {
+                    tc::tma_store_3d_u32(&c.tmS, tc::smem_u32(sm.stg) + (uint32_t)(k * kStgF), u0, b0, c.reverse ? tau : tau + 1);
+                    tc::bulk_commit_group();
+                    tc::bulk_wait_group<0>();                  // the tile is in L2 (and the staging tile reusable)
+                }
+                __syncwarp();
+                FN_STAMP2(s, k * 32 + 9);
+                if (s + 1 < T && tc::elect_one()) {
 #if FN_GRU2_FENCES
                     asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
+                    publish2(P.bar + (ch0 + k) * 16 + rank);
                 }
-            }
-            __syncwarp();
-            if (dbg_on) t12 = clk();
-            if (tc::elect_one()) {
-                if (s + 1 < T) publish2(gflag);
-            }
-            __syncwarp();
-            if (dbg_on) {
-                t10 = clk();
-                long long* dp = P.dbg + (long long)s * 64;
-                dp[8] = t8; dp[9] = t9; dp[12] = t12; dp[10] = t10;
+                __syncwarp();
+                FN_STAMP2(s, k * 32 + 10);
             }
         }
     } else {
         // ------------------------------- gate epilogue (16 warps) ------------------------------------------------
-        constexpr int UT = 16;
+        constexpr int UT = kUT;
         const int q = warp & 3;                                // TMEM lane quarter
-        const int grp = (warp - kEpi0) >> 2;                   // 16-unit group of the pair's 64 units
+        const int grp = (warp - kEpi0) >> 2;                   // 8-unit group of the pair's 32 units
         const int uu = grp * UT, u = u0 + uu;
-        const uint32_t col = (uint32_t)((grp >> 1) * 96 + (grp & 1) * UT);       // column of gate r of this group; z: +32, n: +64
-        const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + col, t_prj = t_acc + N;
+        const uint32_t col = (uint32_t)((grp >> 1) * kNW + (grp & 1) * UT);      // column of gate r of this group; z: + UP/2, n: + UP
+        constexpr uint32_t GS = kUP / 2;                        // column stride between the gates of a half
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + col;
         const int rl = q * 32 + lane, b = b0 + rl;
         const bool row_ok = b < B;
-        const uint32_t stg = tc::smem_u32(sm.stg);
-        float hreg[UT];
-        {
-            float pr[UT], pz[UT], pn[UT];
+        const uint32_t stg = tc::smem_u32(sm.stg) + (kUP == 32 ? swz64(rl, grp) : swz(rl, 2 * grp));
+        const uint32_t stg_hi = tc::smem_u32(sm.stg) + swz(rl, 2 * grp + 1);      // second 16-byte chunk (UP = 64 only)
+        const bool dbg_e = dbg_on && warp == kEpi0;
+        float hreg[kMaxCpp][UT];
+        int id_next[kMaxCpp];
 #pragma unroll
-            for (int j = 0; j < UT; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; hreg[j] = 0.f; }
-            if (row_ok) {
-                if (c.proj) {
-                    const float* pj = c.proj + (long long)b * c.proj_ld + u;
-                    ldf<UT>(pj, pr); ldf<UT>(pj + H, pz); ldf<UT>(pj + 2 * H, pn);
+        for (int k = 0; k < kMaxCpp; ++k) {
+            id_next[k] = 0;
+#pragma unroll
+            for (int j = 0; j < UT; ++j) hreg[k][j] = 0.f;
+            if (k < nact) {
+                const Tc2Chain& c = P.c[ch0 + k];
+                float pr[UT], pz[UT], pn[UT];
+#pragma unroll
+                for (int j = 0; j < UT; ++j) { pr[j] = 0.f; pz[j] = 0.f; pn[j] = 0.f; }
+                if (row_ok) {
+                    if (c.proj) {
+                        const float* pj = c.proj + (long long)b * c.proj_ld + u;
+                        ldf<UT>(pj, pr); ldf<UT>(pj + H, pz); ldf<UT>(pj + 2 * H, pn);
+                    }
+                    uint32_t hw[UT / 2];
+                    ldb_raw<UT>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
+                    unpack<UT>(hw, hreg[k]);
+                    if (c.emb) id_next[k] = c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b];
                 }
-                uint32_t hw[UT / 2];
-                ldb_raw<UT>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
-                unpack<UT>(hw, hreg);
-            }
+                const float* bs = sm.bias + k * 3 * kUP + uu;
 #pragma unroll
-            for (int j = 0; j < UT; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[kUP + uu + j]; }
-            tmem_st<UT>(t_prj, pr); tmem_st<UT>(t_prj + 32, pz); tmem_st<UT>(t_prj + 64, pn);
-            tmem_st_wait();
+                for (int j = 0; j < UT; ++j) { pr[j] += bs[j]; pz[j] += bs[kUP + j]; }
+                const uint32_t tp = t_lane + kAccCols + (uint32_t)(k * kN);
+                tmem_st<UT>(tp, pr); tmem_st<UT>(tp + GS, pz); tmem_st<UT>(tp + 2 * GS, pn);
+            }
         }
-        int id_next = (c.emb && row_ok) ? c.ids[(long long)(c.reverse ? T - 1 : 0) * B + b] : 0;
-        const bool has_in = (c.emb != nullptr) || (c.dense != nullptr);
+        tmem_st_wait();
         for (int s = 0; s < T; ++s) {
-            const int tau = c.reverse ? T - 1 - s : s;
-            const int tau_n = c.reverse ? tau - 1 : tau + 1;
-            // ---- operand that does not depend on the recurrence: fetch before waiting for the MMAs
-            uint32_t ir[UT / 2], iz[UT / 2], in_[UT / 2];
 #pragma unroll
-            for (int j = 0; j < UT / 2; ++j) { ir[j] = 0u; iz[j] = 0u; in_[j] = 0u; }
-            if (row_ok && has_in) {
-                const __nv_bfloat16* src = c.emb ? c.emb + (long long)id_next * 3 * H + u : c.dense + ((long long)tau * B + b) * 3 * H + u;
-                ldb_raw<UT>(src, ir, false); ldb_raw<UT>(src + H, iz, false); ldb_raw<UT>(src + 2 * H, in_, false);
-                if (c.emb && s + 1 < T) id_next = c.ids[(long long)tau_n * B + b];
-            }
-            const bool dbg_e = dbg_on && warp == kEpi0;
-            if (dbg_e) P.dbg[(long long)s * 64 + 5] = clk();
-            tc::mbar_wait_warp(sm.acc_full, s & 1);
-            tc::tc_fence_after();
-            if (dbg_e) P.dbg[(long long)s * 64 + 6] = clk();
-            float r[UT], z[UT], n[UT], g[UT];
-            {
-                float a[UT], p[UT], x[UT];
-                tmem_ld2<UT>(t_acc, a, t_prj, p);
-                unpack<UT>(ir, x);
+            for (int k = 0; k < kMaxCpp; ++k) {
+                if (k >= nact) break;
+                const Tc2Chain& c = P.c[ch0 + k];
+                const int tau = c.reverse ? T - 1 - s : s;
+                const int tau_n = c.reverse ? tau - 1 : tau + 1;
+                // ---- operand that does not depend on the recurrence: fetch before waiting for the MMAs
+                uint32_t ir[UT / 2], iz[UT / 2], in_[UT / 2];
 #pragma unroll
-                for (int j = 0; j < UT; ++j) r[j] = fast_sigmoid(a[j] + p[j] + x[j]);
-                tmem_ld2<UT>(t_acc + 32, a, t_prj + 32, p);
-                unpack<UT>(iz, x);
-#pragma unroll
-                for (int j = 0; j < UT; ++j) z[j] = fast_sigmoid(a[j] + p[j] + x[j]);
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {                   // the n gate in halves of 8 units (register pressure)
-                float a[8], p[8];
-                tmem_ld2<8>(t_acc + 64 + hh * 8, a, t_prj + 64 + hh * 8, p);
-                if (hh == 1) tc::tc_fence_before();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int jj = hh * 8 + j;
-                    const uint32_t w = in_[jj >> 1];
-                    const float x = (jj & 1) ? bf_hi(w) : bf_lo(w);
-                    g[jj] = a[j] + sm.bias[2 * kUP + uu + jj];
-                    n[jj] = fast_tanh(p[j] + x + r[jj] * g[jj]);
-                    hreg[jj] = (1.f - z[jj]) * n[jj] + z[jj] * hreg[jj];
+                for (int j = 0; j < UT / 2; ++j) { ir[j] = 0u; iz[j] = 0u; in_[j] = 0u; }
+                if (row_ok && (c.emb || c.dense)) {
+                    const __nv_bfloat16* src = c.emb ? c.emb + (long long)id_next[k] * 3 * H + u : c.dense + ((long long)tau * B + b) * 3 * H + u;
+                    ldb_raw<UT>(src, ir, false); ldb_raw<UT>(src + H, iz, false); ldb_raw<UT>(src + 2 * H, in_, false);
+                    if (c.emb && s + 1 < T) id_next[k] = c.ids[(long long)tau_n * B + b];
                 }
-            }
-            // new state -> swizzled staging tile -> (store warp) one TMA store + one publish per CTA
-            stage16(stg, rl, uu >> 3, hreg);
-            tc::fence_proxy_async();
-            if (P.dbg != nullptr && blockIdx.x == 0 && lane == 0) P.dbg[(long long)s * 64 + 40 + (warp - kEpi0)] = clk();
-            asm volatile("bar.arrive %0, %1;" ::"n"(kBarStage), "n"((kEW2 + 1) * 32) : "memory");
-            if (row_ok) {
-                if (c.gates) {                                 // off the critical path
-                    stb<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), r);
-                    stb<UT>(c.gates + gate_off(tau, b, H + u, B, 4 * H), z);
-                    stb<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, 4 * H), n);
-                    stb<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, 4 * H), g);
-                }
-                if (s == T - 1 && c.h_final) {
-                    float* hf = c.h_final + (long long)b * c.h_final_ld + u;
+                if (dbg_e) P.dbg[(long long)s * 64 + k * 32 + 5] = clk();
+                tc::mbar_wait_warp(&sm.acc_full[k], s & 1);
+                tc::tc_fence_after();
+                if (dbg_e) P.dbg[(long long)s * 64 + k * 32 + 6] = clk();
+                const uint32_t ta = t_lane + (uint32_t)(k * kN), tp = ta + kAccCols;
+                float r[UT], z[UT], n[UT], g[UT];
+                {
+                    float a[UT], p[UT], x[UT];
+                    tmem_ld2<UT>(ta, a, tp, p);
+                    unpack<UT>(ir, x);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) hf[j] = hreg[j];
+                    for (int j = 0; j < UT; j += 2) sigmoid2(a[j] + p[j] + x[j], a[j + 1] + p[j + 1] + x[j + 1], r[j], r[j + 1]);
+                    tmem_ld2<UT>(ta + GS, a, tp + GS, p);
+                    unpack<UT>(iz, x);
+#pragma unroll
+                    for (int j = 0; j < UT; j += 2) sigmoid2(a[j] + p[j] + x[j], a[j + 1] + p[j + 1] + x[j + 1], z[j], z[j + 1]);
+                    tmem_ld2<UT>(ta + 2 * GS, a, tp + 2 * GS, p);
+                    tc::tc_fence_before();
+                    unpack<UT>(in_, x);
+                    const float* bn = sm.bias + k * 3 * kUP + 2 * kUP + uu;
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) {
+                        g[j] = a[j] + bn[j];
+                        n[j] = fast_tanh(p[j] + x[j] + r[j] * g[j]);
+                        hreg[k][j] = (1.f - z[j]) * n[j] + z[j] * hreg[k][j];
+                    }
                 }
+                // new state -> swizzled staging tile -> (store warp) one TMA store + one publish per CTA and chain
+                sts16(stg + (uint32_t)(k * kStgF), pack2(hreg[k][0], hreg[k][1]), pack2(hreg[k][2], hreg[k][3]), pack2(hreg[k][4], hreg[k][5]),
+                      pack2(hreg[k][6], hreg[k][7]));
+                if constexpr (UT == 16)
+                    sts16(stg_hi, pack2(hreg[k][8], hreg[k][9]), pack2(hreg[k][10], hreg[k][11]), pack2(hreg[k][12], hreg[k][13]),
+                          pack2(hreg[k][14], hreg[k][15]));
+                tc::fence_proxy_async();
+                if (P.dbg != nullptr && blockIdx.x == 0 && lane == 0) P.dbg[(long long)s * 64 + k * 32 + 12 + (warp - kEpi0)] = clk();
+                asm volatile("bar.arrive %0, %1;" ::"r"(kBarStage + k), "n"((kEW2 + 1) * 32) : "memory");
+                if (row_ok) {
+                    if (c.gates) {                             // off the critical path
+                        stb<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), r);
+                        stb<UT>(c.gates + gate_off(tau, b, H + u, B, 4 * H), z);
+                        stb<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, 4 * H), n);
+                        stb<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, 4 * H), g);
+                    }
+                    if (s == T - 1 && c.h_final) {
+                        float* hf = c.h_final + (long long)b * c.h_final_ld + u;
+#pragma unroll
+                        for (int j = 0; j < UT; ++j) hf[j] = hreg[k][j];
+                    }
+                }
+                if (dbg_e) P.dbg[(long long)s * 64 + k * 32 + 11] = clk();
             }
-            if (dbg_e) P.dbg[(long long)s * 64 + 11] = clk();
         }
         tc::tc_fence_before();
     }
@@ -403,58 +451,57 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
 // ---- host -------------------------------------------------------------------------------------------
 struct Plan2 { int kch, stages, kres, wst; size_t smem; bool ok; };
 
-// nkc K chunks of `w_chunk` bytes per CTA; the state ring wants >= 2 stages of kch * 16 KB.
-Plan2 plan2(int nkc, int w_chunk, const char* tag) {
+// Shared-memory plan: `cpp` chains per pair, nkc K chunks of `w_chunk` bytes per chain and CTA, `stg` staging bytes.
+Plan2 plan2(int nkc, int w_chunk, int cpp, int stg, const char* tag, int kch_dflt = 4, int s_dflt = 2, int wst_dflt = 2) {
     Plan2 pl{};
-    static const int kch_env = env_int("FN_GRU2_KCH", 2), s_env = env_int("FN_GRU2_S", 3), wst_env = env_int("FN_GRU2_WST", 2);
+    static const int kch_e = env_int("FN_GRU2_KCH", 0), s_e = env_int("FN_GRU2_S", 0), wst_e = env_int("FN_GRU2_WST", 0);
+    const int kch_env = kch_e ? kch_e : kch_dflt, s_env = s_e ? s_e : s_dflt, wst_env = wst_e ? wst_e : wst_dflt;
     int kch = kch_env == 1 || kch_env == 2 || kch_env == 4 ? kch_env : 2;
     while (kch > 1 && nkc % kch) kch >>= 1;
     pl.kch = kch;
-    const long long budget = (long long)fn_max_smem_optin() - (long long)kSmemTail2 - kStg;
+    const long long budget = (long long)fn_max_smem_optin() - (long long)kSmemTail2 - stg;
     const long long a_stage = (long long)kch * kATile, w_slot = (long long)kch * w_chunk;
-    long long room = budget - (long long)nkc * w_chunk;
-    if (room >= 3 * a_stage) {                                  // the whole half-slice stays resident
+    long long room = budget - (long long)cpp * nkc * w_chunk;
+    if (room >= 3 * a_stage) {                                  // the whole half-slices stay resident
         pl.kres = nkc; pl.wst = 0;
         pl.stages = (int)(room / a_stage);
     } else {
         int S = s_env < 2 ? 2 : s_env, wst = wst_env < 2 ? 2 : wst_env;
         if (wst > kMaxWst) wst = kMaxWst;
-        long long kres = (budget - S * a_stage - wst * w_slot) / w_chunk;
+        long long kres = (budget - S * a_stage - wst * w_slot) / ((long long)cpp * w_chunk);
         if (kres > nkc - kch) kres = nkc - kch;
         kres -= kres % kch;
         if (kres < 0) { pl.ok = false; return pl; }
         pl.kres = (int)kres; pl.wst = wst; pl.stages = S;
     }
     if (pl.stages > kMaxStages) pl.stages = kMaxStages;
-    if (pl.stages > nkc / kch * 2) pl.stages = nkc / kch * 2;
     pl.ok = pl.stages >= 2;
-    pl.smem = (size_t)((long long)pl.kres * w_chunk + pl.wst * w_slot + pl.stages * a_stage) + kStg + kSmemTail2;
+    pl.smem = (size_t)((long long)cpp * pl.kres * w_chunk + pl.wst * w_slot + pl.stages * a_stage) + stg + kSmemTail2;
     static const int verbose = env_int("FN_GRU_VERBOSE", 0);
     if (verbose && pl.ok)
-        fprintf(stderr, "plan2 %s nkc=%d: kch=%d stages=%d kres=%d wst=%d smem=%zu\n", tag, nkc, pl.kch, pl.stages, pl.kres, pl.wst, pl.smem);
+        fprintf(stderr, "plan2 %s nkc=%d cpp=%d: kch=%d stages=%d kres=%d wst=%d smem=%zu\n", tag, nkc, cpp, pl.kch, pl.stages, pl.kres, pl.wst, pl.smem);
     return pl;
 }
 
-int make_tmap_bf16_4d(CUtensorMap* out, const void* base, const cuuint64_t (&dims)[4], const cuuint64_t (&strides_bytes)[3],
-                      const cuuint32_t (&box)[4]) {
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, CUtensorMapSwizzle swz) {
     fn_PFN_encodeTiled enc = fn_get_encode_tiled();
     FN_REQUIRE(enc, "cuTensorMapEncodeTiled entry point unavailable");
-    FN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA 4-D operand alignment");
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
+    FN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand alignment");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%d-d) failed (%d)", rank, (int)r);
     return FN_OK;
 }
 
 template <typename K>
-int launch2(K kernel, const Tc2Launch& P, size_t smem, cudaStream_t st) {
+int launch2(K kernel, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t st) {
     const void* fn = (const void*)kernel;
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    const int ctas = P.n_chains * P.npairs * 2;
+    const int ctas = pairs * 2;
     cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(kThreads2);
     cfg.dynamicSmemBytes = smem;
@@ -468,7 +515,7 @@ int launch2(K kernel, const Tc2Launch& P, size_t smem, cudaStream_t st) {
     cfg.numAttrs = 2;
     int max_clusters = 0;
     FN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
-    FN_REQUIRE(max_clusters * 2 >= ctas, "fn_gru_seq_bf16: %d CTAs in pairs are not co-resident (max %d pairs)", ctas, max_clusters);
+    FN_REQUIRE(max_clusters >= pairs, "fn_gru_seq_bf16: %d CTA pairs are not co-resident (max %d)", pairs, max_clusters);
     void* args[] = {(void*)&P};
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {                                  // cooperative + cluster refused: residency was checked above
@@ -480,14 +527,31 @@ int launch2(K kernel, const Tc2Launch& P, size_t smem, cudaStream_t st) {
     return FN_OK;
 }
 
+// Geometry of a launch of n chains of hidden size H: UP = 32 with one chain per pair if every chain can have its own H/32
+// pairs; else UP = 64 (one chain per pair, H/64 pairs each) or UP = 32 with two chains per pair (FN_GRU2_GEO = 64 | 32).
+struct Geom { int up, cpp; };
+Geom pick_geo(int n, int H) {
+    static const int force = env_int("FN_GRU2_GEO", 64);
+    const int max_pairs = fn_num_sms() / 2;
+    if (n * (H / 32) <= max_pairs) return {32, 1};
+    if (force == 64 && n * (H / 64) <= max_pairs) return {64, 1};
+    return {32, 2};
+}
+template <int UP>
+int launch_fwd(int kch, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t st) {
+    if (kch == 4) return launch2(gru2_fwd_kernel<UP, 4>, P, pairs, smem, st);
+    if (kch == 2) return launch2(gru2_fwd_kernel<UP, 2>, P, pairs, smem, st);
+    return launch2(gru2_fwd_kernel<UP, 1>, P, pairs, smem, st);
+}
+
 }  // namespace
 
 bool fn_gru2_eligible(bool bwd, int n_chains, int B, int H) {
     static const int on = env_int("FN_GRU_V2", 1);
     if (!on || (bwd && !(on & 2))) return false;
-    if (B <= 128 || B > 256 || H % kUP || H < 128) return false;
-    if (2 * (H / kUP) > fn_num_sms()) return false;
-    return plan2(H / 64, 96 * 128, "fwd").ok;
+    if (B <= 128 || B > 256 || H % 64 || H < 128) return false;
+    if (H / 64 > fn_num_sms() / 2) return false;               // one chain must fit the machine
+    return plan2(H / 64, Geo<32>::kWCh, 2, kStgAll, "fwd").ok;
 }
 
 int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
@@ -495,13 +559,16 @@ int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int
     FN_REQUIRE(!bwd, "fn_gru2_run: backward not built yet");
     FN_REQUIRE(chains && n_chains > 0 && barrier_ws && ws_bytes >= (size_t)64 * n_chains, "fn_gru_seq_bf16: bad arguments");
     FN_CHECK_CUDA(cudaMemsetAsync(barrier_ws, 0, (size_t)64 * n_chains, st));
-    const int npairs = H / kUP, nkc = H / 64;
-    const Plan2 pl = plan2(nkc, 96 * 128, "fwd");
-    FN_REQUIRE(pl.ok, "fn_gru_seq_bf16: no shared-memory plan for H=%d", H);
-    const int per_launch = fn_num_sms() / (2 * npairs) < kMaxChainsTc ? fn_num_sms() / (2 * npairs) : kMaxChainsTc;
+    const int nkc = H / 64, max_pairs = fn_num_sms() / 2;
     int done = 0;
     while (done < n_chains) {
-        const int group = n_chains - done < per_launch ? n_chains - done : per_launch;
+        int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc;
+        Geom g = pick_geo(group, H);
+        while (((group + g.cpp - 1) / g.cpp) * (H / g.up) > max_pairs) { --group; g = pick_geo(group, H); }   // (group >= 1 fits: fn_gru2_eligible)
+        const int ppc = H / g.up, cpp = g.cpp, w_chunk = g.up == 64 ? Geo<64>::kWCh : Geo<32>::kWCh;
+        // ring defaults from the config-3 sweeps: N = 96 wants 64 KB state boxes (everything streamed), N = 192 32 KB boxes
+        const Plan2 pl = g.up == 64 ? plan2(nkc, w_chunk, cpp, kStgAll, "fwd64", 2, 3, 2) : plan2(nkc, w_chunk, cpp, kStgAll, "fwd32", 4, 2, 2);
+        FN_REQUIRE(pl.ok, "fn_gru_seq_bf16: no shared-memory plan for H=%d", H);
         Tc2Launch P;
         memset(&P, 0, sizeof(P));
         for (int i = 0; i < group; ++i) {
@@ -511,19 +578,24 @@ int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int
             FN_REQUIRE(!s.emb || s.ids, "fn_gru_seq_fwd_bf16: chain %d has emb without ids", done + i);
             FN_REQUIRE(!(s.emb && s.dense), "fn_gru_seq_fwd_bf16: chain %d has both a token and a dense input", done + i);
             int rc;
-            {   // W_hh [3H][H] as (k in chunk, unit, gate, K chunk): one box = this CTA's 3 x 32 rows of KCH chunks
+            {   // W_hh [3H][H] as (k in chunk, unit, gate, K chunk): one box = this CTA's 3 x 16 rows of KCH chunks (KCH x 6 KB)
                 const cuuint64_t dims[4] = {64, (cuuint64_t)H, 3, (cuuint64_t)nkc};
                 const cuuint64_t str[3] = {(cuuint64_t)H * 2, (cuuint64_t)H * H * 2, 128};
-                const cuuint32_t box[4] = {64, 32, 3, (cuuint32_t)pl.kch};
-                if ((rc = make_tmap_bf16_4d(&d.tmW, s.w_hh, dims, str, box))) return rc;
+                const cuuint32_t box[4] = {64, (cuuint32_t)g.up / 2, 3, (cuuint32_t)pl.kch};
+                if ((rc = make_tmap_bf16_nd(&d.tmW, s.w_hh, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
             }
-            {   // hsx [T+1][B][H] as (k in chunk, row, K chunk, slab)
+            {   // hsx [T+1][B][H] as (k in chunk, row, K chunk, slab): one box = 128 rows of KCH chunks (KCH x 16 KB)
                 const cuuint64_t dims[4] = {64, (cuuint64_t)B, (cuuint64_t)nkc, (cuuint64_t)T + 1};
                 const cuuint64_t str[3] = {(cuuint64_t)H * 2, 128, (cuuint64_t)B * H * 2};
                 const cuuint32_t box[4] = {64, 128, (cuuint32_t)pl.kch, 1};
-                if ((rc = make_tmap_bf16_4d(&d.tmA, s.hsx, dims, str, box))) return rc;
+                if ((rc = make_tmap_bf16_nd(&d.tmA, s.hsx, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
             }
-            if ((rc = fn_make_tmap_bf16_3d(&d.tmS, s.hsx, T + 1, B, H, H, 128, 64))) return rc;
+            {   // store of the new state tile: (unit, row, slab), box 32 units x 128 rows (64-byte rows)
+                const cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)T + 1};
+                const cuuint64_t str[2] = {(cuuint64_t)H * 2, (cuuint64_t)B * H * 2};
+                const cuuint32_t box[3] = {(cuuint32_t)g.up, 128, 1};
+                if ((rc = make_tmap_bf16_nd(&d.tmS, s.hsx, 3, dims, str, box, g.up == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+            }
             d.b_hh = s.b_hh; d.emb = (const __nv_bfloat16*)s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
             d.dense = (const __nv_bfloat16*)s.dense;
             d.hsx = (__nv_bfloat16*)s.hsx; d.gates = (__nv_bfloat16*)s.gates;
@@ -531,13 +603,11 @@ int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int
             d.reverse = s.reverse;
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
-        P.n_chains = group; P.npairs = npairs; P.B = B; P.T = T; P.H = H;
+        P.n_chains = group; P.ppc = ppc; P.cpp = cpp; P.B = B; P.T = T; P.H = H;
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
         P.dbg = fn_gru_dbg_ptr();
-        int rc;
-        if (pl.kch == 4) rc = launch2(gru2_fwd_kernel<4>, P, pl.smem, st);
-        else if (pl.kch == 2) rc = launch2(gru2_fwd_kernel<2>, P, pl.smem, st);
-        else rc = launch2(gru2_fwd_kernel<1>, P, pl.smem, st);
+        const int pairs = ((group + cpp - 1) / cpp) * ppc;
+        const int rc = g.up == 64 ? launch_fwd<64>(pl.kch, P, pairs, pl.smem, st) : launch_fwd<32>(pl.kch, P, pairs, pl.smem, st);
         if (rc != FN_OK) return rc;
         done += group;
     }

@@ -33,13 +33,14 @@ torch.cuda.synchronize()
 LIB.call("fn_gru_debug_timeline", None)
 print(f"forward launch (incl. setup kernels): {e0.elapsed_time(e1):.3f} ms = {e0.elapsed_time(e1) / T * 1e3:.2f} us/step")
 d = dbg.view(T + 1, 64).cpu()
-names = {0: "ld:start", 1: "ld:flag", 2: "ld:issued", 4: "mma:last commit", 5: "epi:x loaded", 6: "epi:acc ready",
-         8: "st:bar", 9: "st:stored", 12: "st:fenced", 10: "st:published", 11: "epi:gates stored"}
-nst = 16
+names = {1: "ld:flag", 2: "ld:issued", 3: "mma:first data", 4: "mma:last commit", 5: "epi:x loaded", 6: "epi:acc ready",
+         9: "st:stored", 10: "st:published", 11: "epi:gates stored"}
 for s in range(T // 2, min(T // 2 + 3, T - 1)):
     t0 = int(d[s, 0])
-    print(f"step {s}: " + "  ".join(f"{names[k]}={int(d[s, k]) - t0}" for k in sorted(names) if k))
-    print("      mma stage data ready: " + " ".join(str(int(d[s, 16 + j]) - t0) for j in range(nst) if int(d[s, 16 + j])))
-    print("      mma stage weights ready: " + " ".join(str(int(d[s, 32 + j]) - t0) for j in range(nst) if int(d[s, 32 + j])))
-    print("      epi warps staged: " + " ".join(str(int(d[s, 40 + j]) - t0) for j in range(16)))
+    for k in range(2):
+        o = k * 32
+        if not int(d[s, o + 1]):
+            continue
+        print(f"step {s} chain {k}: ld:start={int(d[s, o]) - t0}  " + "  ".join(f"{names[e]}={int(d[s, o + e]) - t0}" for e in sorted(names)))
+        print("      epi warps staged: " + " ".join(str(int(d[s, o + 12 + j]) - t0) for j in range(16)))
     print(f"   step period: {int(d[s + 1, 0]) - t0} cycles")
