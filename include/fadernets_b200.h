@@ -184,6 +184,15 @@ int fn_decode_greedy_bf16(const void* w_hh1, const float* b_hh1, const void* emb
  * events into `device_buffer` ((T+1)*2*16 int64); NULL switches it off. */
 int fn_gru_debug_timeline(void* device_buffer);
 
+/* Index validation.  The reference's F.nll_loss / nn.Embedding / Embedding lookups (trainer_gmm.py:131-136,156,182;
+ * gmm_model.py:84,109,132) raise on an out-of-range index.  Here every kernel that consumes an index CLAMPS it (no
+ * out-of-bounds access is possible); these two entry points COUNT offending entries into `bad_count` (device int32,
+ * accumulated, never reset by the library) so that the host mirror raises IndexError at its next synchronisation.
+ * fn_check_index_i64 only counts (user-owned targets / labels); fn_clamp_index_i32 also clamps in place (the library's own
+ * time-major id buffers that feed the embedding gathers). */
+int fn_check_index_i64(const int64_t* idx, long long n, long long hi, int32_t* bad_count, void* stream);
+int fn_clamp_index_i32(int32_t* idx, long long n, int hi, int32_t* bad_count, void* stream);
+
 /* fp32 -> bf16 with arbitrary strides: dst[r*ld_dst + c] = bf16(src[r*s_r + c*s_c]) (s_r/s_c in
  * elements; s_c != 1 gives the transposed copy W_hh^T used by BPTT). */
 int fn_cast_bf16(const float* src, long long s_r, long long s_c, void* dst, long long ld_dst, long long rows,

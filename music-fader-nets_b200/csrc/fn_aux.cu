@@ -57,7 +57,7 @@ __global__ void onehot_to_ids_kernel(const float* __restrict__ oh, int B, int T,
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (lane == 0) ids_tm[(long long)t * B + b] = bi;
+    if (lane == 0) ids_tm[(long long)t * B + b] = bi == 0x7fffffff ? 0 : bi;     // a row without a maximum (all NaN / -inf) still yields a valid id
 }
 
 __global__ void ids_to_onehot_kernel(const int64_t* __restrict__ ids, long long rows, int V, float* __restrict__ oh) {
@@ -76,6 +76,29 @@ __global__ void ids_to_tm_kernel(const int64_t* __restrict__ ids, int B, int T, 
     const int t = (int)(i / B), b = (int)(i % B);
     const int ts = t - shift;
     out[i] = ts < 0 ? start : (int)ids[(long long)b * T + ts];
+}
+
+// Index validation (the reference's F.nll_loss / nn.Embedding raise on an out-of-range index; here the ids are clamped so
+// that no kernel ever reads or writes out of bounds, and counted so that the host mirror can raise at its next sync).
+__global__ void check_index_i64_kernel(const int64_t* __restrict__ idx, long long n, long long hi, int32_t* __restrict__ bad) {
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = idx[i];
+        c += (v < 0 || v >= hi) ? 1 : 0;
+    }
+    if (__syncthreads_or(c)) {
+        if (c) atomicAdd(bad, c);
+    }
+}
+__global__ void clamp_index_i32_kernel(int32_t* __restrict__ idx, long long n, int hi, int32_t* __restrict__ bad) {
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = idx[i];
+        if (v < 0 || v >= hi) { idx[i] = v < 0 ? 0 : hi - 1; ++c; }
+    }
+    if (__syncthreads_or(c)) {
+        if (c) atomicAdd(bad, c);
+    }
 }
 
 __global__ void transpose_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
@@ -266,6 +289,23 @@ extern "C" int fn_ids_to_time_major(const int64_t* ids, int B, int T, int shift,
     FN_LAUNCH_CHECK();
     return FN_OK;
 }
+extern "C" int fn_check_index_i64(const int64_t* idx, long long n, long long hi, int32_t* bad_count, void* stream) {
+    FN_REQUIRE(idx && bad_count && n >= 0 && hi > 0, "fn_check_index_i64: bad args");
+    if (n == 0) return FN_OK;
+    const int blocks = (int)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+    check_index_i64_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, n, hi, bad_count);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+extern "C" int fn_clamp_index_i32(int32_t* idx, long long n, int hi, int32_t* bad_count, void* stream) {
+    FN_REQUIRE(idx && bad_count && n >= 0 && hi > 0, "fn_clamp_index_i32: bad args");
+    if (n == 0) return FN_OK;
+    const int blocks = (int)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+    clamp_index_i32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, n, hi, bad_count);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+
 extern "C" int fn_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols,
                                 int accumulate, void* stream) {
     FN_REQUIRE(src && dst && rows > 0 && cols > 0, "fn_transpose_f32: bad args");

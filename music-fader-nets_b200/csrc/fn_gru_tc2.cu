@@ -43,7 +43,8 @@ struct Tc2Launch {
     Tc2Chain c[kMaxChainsTc];
     unsigned* bar;         // per chain 16 counters (one per batch tile), zeroed by the host
     long long* dbg;        // profiling aid (fn_gru_debug_timeline): [step][64] clock64 stamps of CTA 0, or NULL
-    int n_chains, ppc, cpp, B, T, H;   // ppc: pairs per chain (H / 32); cpp: chains per pair (1 or 2)
+    int n_chains, ppc, cpp, B, T, H;   // ppc: pairs per chain (H / UP); cpp: chains per pair (1 or 2)
+    int mc;                            // pairs per cluster (1, 2 or 4): same-rank CTAs of a cluster share ONE multicast load of each state chunk
     int stages, kres, wst; // state-ring stages (of KCH chunks); resident weight chunks; weight-ring slots (of KCH chunks)
 };
 
@@ -146,7 +147,11 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
     const Smem2 sm = carve2(smem_raw, cpp * kres * kWCh, WST * (int)w_slot, S * (int)a_stage, kStgAll);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = tc::cluster_ctarank();               // 0 = leader (issues the MMAs); this CTA owns batch tile `rank`
+    const uint32_t crank = tc::cluster_ctarank();
+    const uint32_t rank = crank & 1u;                          // 0 = leader of its pair (issues the MMAs); this CTA owns batch tile `rank`
+    const int pp = (int)(crank >> 1), mc = P.mc;               // pair index inside the cluster; pairs per cluster
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pp));     // both CTAs of this pair
+    const uint16_t all_mask = (uint16_t)((1u << (2 * mc)) - 1u);
     const int pair = blockIdx.x >> 1;
     const int group = pair / P.ppc, slice = pair % P.ppc;
     const int ch0 = group * cpp;                               // first chain of this pair
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
 
     if (warp == 0 && lane == 0) {
         for (int k = 0; k < nact; ++k) { tc::prefetch_tmap(&P.c[ch0 + k].tmW); tc::prefetch_tmap(&P.c[ch0 + k].tmA); tc::prefetch_tmap(&P.c[ch0 + k].tmS); }
-        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], 1); }
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], (uint32_t)mc); }   // a slot is free when EVERY pair of the cluster has consumed it
         for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
         tc::mbar_init(sm.wbar, 1);
         for (int k = 0; k < kMaxCpp; ++k) tc::mbar_init(&sm.acc_full[k], 1);
@@ -184,6 +189,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
         // are slower still (8 KB x 4 lanes: 50 B/clk) -- so the boxes are as big as the ring allows.
         const uint32_t full0 = tc::smem_u32(sm.full), full_l = full0 & tc::kPeerBitMask, empty0 = tc::smem_u32(sm.empty);
         const uint32_t a0 = tc::smem_u32(sm.A);
+        uint16_t mc_mask = 0;
+        for (int q = 0; q < mc; ++q) mc_mask |= (uint16_t)(1u << (2 * q + (int)rank));
         if (kres > 0) {
             if (rank == 0 && lane == 0) tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(2 * nact * kres * kWCh));
             __syncwarp();
@@ -213,7 +220,10 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                     tc::mbar_wait_u32(empty0 + st * 8u, ph);
                     if (tc::elect_one()) {
                         if (rank == 0) tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, 2 * a_stage);
-                        tc::tma_load_4d_2cta_u32(a0 + st * a_stage, &c.tmA, full_l + st * 8u, 0, b0, kc, slab);
+                        if (mc == 1) tc::tma_load_4d_2cta_u32(a0 + st * a_stage, &c.tmA, full_l + st * 8u, 0, b0, kc, slab);
+                        else         // this CTA's share of the stage (KCH / mc chunks), delivered to the same-rank CTA of every pair of the cluster
+                            tc::tma_load_4d_2cta_mc_u32(a0 + st * a_stage + (uint32_t)pp * (a_stage / (uint32_t)mc), &c.tmA, full_l + st * 8u, 0, b0,
+                                                        kc + pp * (KCH / mc), slab, mc_mask);
                     }
                     __syncwarp();
                     kc += KCH;
@@ -254,9 +264,9 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                         if (j == 0) FN_STAMP2(i, k * 32 + 3);
                         if (tc::elect_one()) {
                             issue(d_tmem, adesc0 + (uint64_t)(st * (a_stage >> 4)), wdesc0 + (uint64_t)(ws * (w_slot >> 4)), j == 0);
-                            tc::umma_commit_2cta_mc_u32(wempty0 + ws * 8u, 3);
-                            tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, 3);
-                            if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf0 + k * 8u, 3);
+                            tc::umma_commit_2cta_mc_u32(wempty0 + ws * 8u, pair_mask);
+                            tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, all_mask);
+                            if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf0 + k * 8u, pair_mask);
                         }
                         __syncwarp();
                         if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
@@ -269,8 +279,8 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                         if (j == 0) FN_STAMP2(i, k * 32 + 3);
                         if (tc::elect_one()) {
                             issue(d_tmem, adesc0 + (uint64_t)(st * (a_stage >> 4)), bd, j == 0);
-                            tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, 3);
-                            if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf0 + k * 8u, 3);
+                            tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, all_mask);
+                            if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf0 + k * 8u, pair_mask);
                         }
                         __syncwarp();
                         bd += (uint64_t)(w_slot >> 4);
@@ -448,13 +458,289 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
     }
 }
 
+// =====================================================================================================
+// Backward (BPTT).  Iteration i = 0..T handles step s = T-1-i (s = -1 finishes dh0).  A pair owns 64 units: the product
+//   dh_prev[256 rows x 64 units] = dg3[256 x 3H] * W_hh[3H x 64 units],  dg3 = (dr, dz, dn*r) of the step above,
+// is ONE accumulator of 64 columns (M = 256, N = 64, K = 3H); CTA r holds 32 rows of W_hh^T (4 KB per 64-wide K chunk,
+// resident for its first `kres` chunks, the rest re-streamed) and streams the gate gradients of batch tile r
+// (768 KB per step at H = 1024 -- shared with the same-rank CTAs of its cluster by multicast).  The epilogue turns the
+// accumulator + carry + incoming gradients into (dr, dz, dn, dn*r) of its (row, 16 units), staged as four 128B-swizzled
+// [128 x 64] tiles -- in the state ring itself, which is idle between a step's last MMA and the hand-over -- and written
+// by ONE 4-D TMA store (64 KB) into the dg stream, followed by one publish per CTA.
+// =====================================================================================================
+constexpr int kUPB = 64, kNB = 64, kWChB = 32 * 128;          // units per pair, MMA N, bytes of one K chunk of a CTA's 32 weight rows
+
+template <int KCH>
+__global__ void __launch_bounds__(kThreads2, 1) gru2_bwd_kernel(const __grid_constant__ Tc2Launch P) {
+    constexpr uint32_t kTmemCols = 64;
+    constexpr uint32_t a_stage = KCH * kATile, w_slot = KCH * kWChB;
+    extern __shared__ uint8_t smem_raw[];
+    const int H = P.H, B = P.B, T = P.T, S = P.stages, WST = P.wst, kres = P.kres;
+    const int nkc = 3 * H / 64, nst = nkc / KCH, nsst = (nkc - kres) / KCH;
+    const int gap0 = 2 * H / 64, gap = H / 64;                 // K chunk kc >= gap0 reads dg column chunk kc + gap (skips dn)
+    const Smem2 sm = carve2(smem_raw, kres * kWChB, WST * (int)w_slot, S * (int)a_stage, 0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = tc::cluster_ctarank();
+    const uint32_t rank = crank & 1u;
+    const int pp = (int)(crank >> 1), mc = P.mc;
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pp));
+    const uint16_t all_mask = (uint16_t)((1u << (2 * mc)) - 1u);
+    const int pair = blockIdx.x >> 1;
+    const int chain = pair / P.ppc, slice = pair % P.ppc;
+    const Tc2Chain& c = P.c[chain];
+    unsigned* gflag = P.bar + chain * 16 + rank;
+    const int u0 = slice * kUPB, b0 = (int)rank * 128;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&c.tmW); tc::prefetch_tmap(&c.tmA); tc::prefetch_tmap(&c.tmS);
+        for (int i = 0; i < S; ++i) { tc::mbar_init(&sm.full[i], 1); tc::mbar_init(&sm.empty[i], (uint32_t)mc); }
+        for (int i = 0; i < WST; ++i) { tc::mbar_init(&sm.wfull[i], 1); tc::mbar_init(&sm.wempty[i], 1); }
+        tc::mbar_init(sm.wbar, 1); tc::mbar_init(&sm.acc_full[0], 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc_2cta(sm.tmem_slot, kTmemCols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------- gate-gradient loader (both CTAs: own batch tile) -----------------------
+        const uint32_t full0 = tc::smem_u32(sm.full), full_l = full0 & tc::kPeerBitMask, empty0 = tc::smem_u32(sm.empty);
+        const uint32_t a0 = tc::smem_u32(sm.A);
+        uint16_t mc_mask = 0;
+        for (int q = 0; q < mc; ++q) mc_mask |= (uint16_t)(1u << (2 * q + (int)rank));
+        if (kres > 0) {
+            if (rank == 0 && lane == 0) tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(2 * kres * kWChB));
+            __syncwarp();
+            const uint32_t wbar_l = tc::smem_u32(sm.wbar) & tc::kPeerBitMask;
+            for (int i = lane; i < kres / KCH; i += 32)
+                tc::tma_load_4d_2cta_u32(tc::smem_u32(sm.W) + (uint32_t)(i * KCH * kWChB), &c.tmW, wbar_l, 0, u0 + (int)rank * 32, i * KCH, 0);
+        }
+        __syncwarp();
+        uint32_t st = 0, ph = 1;
+        for (int i = 1; i <= T; ++i) {
+            const int slab = c.reverse ? i - 1 : T - i;        // the gate gradient of step s+1 (s = T-1-i), by time
+            fn_spin_until(gflag, (unsigned)(P.ppc * i));
+#if FN_GRU2_FENCES
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+            int kc = kres;
+            for (int j = 0; j < nst; ++j) {
+                if (j == nsst) kc = 0;
+                const int cc = (kc >= gap0 ? kc + gap : kc) + pp * (KCH / mc);
+                tc::mbar_wait_u32(empty0 + st * 8u, ph);
+                if (tc::elect_one()) {
+                    if (rank == 0) tc::mbar_arrive_expect_tx_u32(full0 + st * 8u, 2 * a_stage);
+                    if (mc == 1) tc::tma_load_4d_2cta_u32(a0 + st * a_stage, &c.tmA, full_l + st * 8u, 0, b0, cc, slab);
+                    else tc::tma_load_4d_2cta_mc_u32(a0 + st * a_stage + (uint32_t)pp * (a_stage / (uint32_t)mc), &c.tmA, full_l + st * 8u, 0, b0, cc,
+                                                     slab, mc_mask);
+                }
+                __syncwarp();
+                kc += KCH;
+                if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer (leader only) -----------------------------------------------
+        if (rank == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(256, kNB, 0, 0);
+            if (kres > 0) tc::mbar_wait(sm.wbar, 0);
+            const uint32_t full0 = tc::smem_u32(sm.full), empty0 = tc::smem_u32(sm.empty);
+            const uint32_t wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty), accf = tc::smem_u32(sm.acc_full);
+            const uint64_t adesc0 = tc::make_sdesc(tc::smem_u32(sm.A), 16, 1024);
+            const uint64_t bdesc0 = tc::make_sdesc(tc::smem_u32(sm.W), 16, 1024);
+            const uint64_t wdesc0 = tc::make_sdesc(tc::smem_u32(sm.WR), 16, 1024);
+            uint32_t st = 0, ph = 0, ws = 0, wph = 0;
+            auto issue = [&](uint64_t ad, uint64_t bd, bool first) {
+#pragma unroll
+                for (int q = 0; q < KCH; ++q) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc::umma_f16_2cta(tmem_base, ad + (uint64_t)(q * (kATile >> 4) + 2 * kk), bd + (uint64_t)(q * (kWChB >> 4) + 2 * kk), idesc,
+                                          (q | kk) ? 1u : (first ? 0u : 1u));
+                }
+            };
+            for (int i = 1; i <= T; ++i) {
+                for (int j = 0; j < nsst; ++j) {
+                    tc::mbar_wait_u32(wfull0 + ws * 8u, wph);
+                    tc::mbar_wait_u32(full0 + st * 8u, ph);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        issue(adesc0 + (uint64_t)(st * (a_stage >> 4)), wdesc0 + (uint64_t)(ws * (w_slot >> 4)), j == 0);
+                        tc::umma_commit_2cta_mc_u32(wempty0 + ws * 8u, pair_mask);
+                        tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, all_mask);
+                        if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf, pair_mask);
+                    }
+                    __syncwarp();
+                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                }
+                uint64_t bd = bdesc0;
+                for (int j = nsst; j < nst; ++j) {
+                    tc::mbar_wait_u32(full0 + st * 8u, ph);
+                    tc::tc_fence_after();
+                    if (tc::elect_one()) {
+                        issue(adesc0 + (uint64_t)(st * (a_stage >> 4)), bd, j == 0);
+                        tc::umma_commit_2cta_mc_u32(empty0 + st * 8u, all_mask);
+                        if (j == nst - 1) tc::umma_commit_2cta_mc_u32(accf, pair_mask);
+                    }
+                    __syncwarp();
+                    bd += (uint64_t)(w_slot >> 4);
+                    if (++st == (uint32_t)S) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------- streamed part of the weight half (both CTAs) ---------------------------
+        if (nsst > 0) {
+            const uint32_t wr0 = tc::smem_u32(sm.WR), wfull0 = tc::smem_u32(sm.wfull), wempty0 = tc::smem_u32(sm.wempty);
+            const uint32_t wfull_l = wfull0 & tc::kPeerBitMask;
+            uint32_t ws = 0, wph = 1;
+            for (int i = 1; i <= T; ++i) {
+                for (int j = 0; j < nsst; ++j) {
+                    tc::mbar_wait_u32(wempty0 + ws * 8u, wph);
+                    if (tc::elect_one()) {
+                        if (rank == 0) tc::mbar_arrive_expect_tx_u32(wfull0 + ws * 8u, 2 * w_slot);
+                        tc::tma_load_4d_2cta_u32(wr0 + ws * w_slot, &c.tmW, wfull_l + ws * 8u, 0, u0 + (int)rank * 32, kres + j * KCH, 0);
+                    }
+                    __syncwarp();
+                    if (++ws == (uint32_t)WST) { ws = 0; wph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------- store + publish (iterations 0 .. T-1 produce a gate-gradient tile) ------
+        for (int i = 0; i < T; ++i) {
+            const int s = T - 1 - i;
+            const int tau = c.reverse ? T - 1 - s : s;
+            asm volatile("bar.sync %0, %1;" ::"n"(kBarStage), "n"((kEW2 + 1) * 32) : "memory");
+            if (tc::elect_one()) {
+                tc::tma_store_4d_u32(&c.tmS, tc::smem_u32(sm.A), u0, b0, 0, tau);
+                tc::bulk_commit_group();
+                tc::bulk_wait_group<0>();
+#if FN_GRU2_FENCES
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+                publish2(gflag);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------- gate-gradient epilogue (16 warps) --------------------------------------
+        constexpr int UT = 16;
+        const int q = warp & 3, grp = (warp - kEpi0) >> 2;
+        const int uu = grp * UT, u = u0 + uu;
+        const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)uu;
+        const int rl = q * 32 + lane, b = b0 + rl;
+        const bool row_ok = b < B;
+        const uint32_t stg0 = tc::smem_u32(sm.A) + swz(rl, 2 * grp), stg1 = tc::smem_u32(sm.A) + swz(rl, 2 * grp + 1);
+        float carry[UT];
+#pragma unroll
+        for (int j = 0; j < UT; ++j) carry[j] = 0.f;
+        for (int i = 0; i <= T; ++i) {
+            const int s = T - 1 - i;
+            const int tau = c.reverse ? T - 1 - s : s;
+            const long long row = (long long)tau * B + b;
+            // ---- saved forward values and incoming gradients: fetch before waiting for the MMAs
+            uint32_t wr[UT / 2], wz[UT / 2], wn[UT / 2], wg[UT / 2], wh[UT / 2];
+            float din[UT];
+#pragma unroll
+            for (int j = 0; j < UT / 2; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
+#pragma unroll
+            for (int j = 0; j < UT; ++j) din[j] = 0.f;
+            if (row_ok && s >= 0) {
+                ldb_raw<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), wr, false);
+                ldb_raw<UT>(c.gates + gate_off(tau, b, H + u, B, 4 * H), wz, false);
+                ldb_raw<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, 4 * H), wn, false);
+                ldb_raw<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, 4 * H), wg, false);
+                ldb_raw<UT>(c.hsx + (row + (c.reverse ? B : 0)) * H + u, wh, false);       // the state before step s
+                if (c.dhs) {
+                    if (c.dhs_f32) ldf<UT>(reinterpret_cast<const float*>(c.dhs) + row * H + u, din);
+                    else {
+                        uint32_t wd[UT / 2];
+                        ldb_raw<UT>(reinterpret_cast<const __nv_bfloat16*>(c.dhs) + row * H + u, wd, false);
+                        unpack<UT>(wd, din);
+                    }
+                }
+                if (s == T - 1 && c.dh_final) {
+                    const float* df = c.dh_final + (long long)b * c.dh_final_ld + u;
+#pragma unroll
+                    for (int j = 0; j < UT; ++j) din[j] += __ldg(df + j);
+                }
+            }
+            float dh[UT];
+            if (i > 0) {
+                tc::mbar_wait_warp(&sm.acc_full[0], (i - 1) & 1);
+                tc::tc_fence_after();
+                tmem_ld<UT>(t_acc, dh);
+                tc::tc_fence_before();
+            } else {
+#pragma unroll
+                for (int j = 0; j < UT; ++j) dh[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < UT; ++j) dh[j] += carry[j] + din[j];
+            if (s < 0) {
+                if (row_ok) stf<UT>(c.dh0 + (long long)b * H + u, dh);
+                break;
+            }
+            // (dr, dz, dn, dn*r) of this thread's 16 units, gate by gate straight into the staging tiles
+            uint32_t o[UT / 2];
+#define FN_STAGE_GATE(gidx)                                                                 \
+            sts16(stg0 + (gidx) * kATile, o[0], o[1], o[2], o[3]);                          \
+            sts16(stg1 + (gidx) * kATile, o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int j = 0; j < UT; j += 2) {                  // dz = dh (h_prev - n) z (1 - z);   carry = dh z
+                const float z0 = bf_lo(wz[j >> 1]), z1 = bf_hi(wz[j >> 1]), n0 = bf_lo(wn[j >> 1]), n1 = bf_hi(wn[j >> 1]);
+                const float h0 = bf_lo(wh[j >> 1]), h1 = bf_hi(wh[j >> 1]);
+                o[j >> 1] = pack2(dh[j] * (h0 - n0) * z0 * (1.f - z0), dh[j + 1] * (h1 - n1) * z1 * (1.f - z1));
+                carry[j] = dh[j] * z0; carry[j + 1] = dh[j + 1] * z1;
+                dh[j] = dh[j] * (1.f - z0) * (1.f - n0 * n0);  // dn_pre
+                dh[j + 1] = dh[j + 1] * (1.f - z1) * (1.f - n1 * n1);
+            }
+            FN_STAGE_GATE(1)
+#pragma unroll
+            for (int j = 0; j < UT; j += 2) o[j >> 1] = pack2(dh[j], dh[j + 1]);                       // dn_pre
+            FN_STAGE_GATE(2)
+#pragma unroll
+            for (int j = 0; j < UT; j += 2) {                  // dn_pre * r
+                const float r0 = bf_lo(wr[j >> 1]), r1 = bf_hi(wr[j >> 1]);
+                o[j >> 1] = pack2(dh[j] * r0, dh[j + 1] * r1);
+            }
+            FN_STAGE_GATE(3)
+#pragma unroll
+            for (int j = 0; j < UT; j += 2) {                  // dr = dn_pre g r (1 - r)
+                const float r0 = bf_lo(wr[j >> 1]), r1 = bf_hi(wr[j >> 1]), g0 = bf_lo(wg[j >> 1]), g1 = bf_hi(wg[j >> 1]);
+                o[j >> 1] = pack2(dh[j] * g0 * r0 * (1.f - r0), dh[j + 1] * g1 * r1 * (1.f - r1));
+            }
+            FN_STAGE_GATE(0)
+#undef FN_STAGE_GATE
+            tc::fence_proxy_async();
+            asm volatile("bar.arrive %0, %1;" ::"n"(kBarStage), "n"((kEW2 + 1) * 32) : "memory");
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    tc::cluster_sync();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_2cta(tmem_base, kTmemCols);
+    }
+}
+
 // ---- host -------------------------------------------------------------------------------------------
 struct Plan2 { int kch, stages, kres, wst; size_t smem; bool ok; };
 
 // Shared-memory plan: `cpp` chains per pair, nkc K chunks of `w_chunk` bytes per chain and CTA, `stg` staging bytes.
 Plan2 plan2(int nkc, int w_chunk, int cpp, int stg, const char* tag, int kch_dflt = 4, int s_dflt = 2, int wst_dflt = 2) {
     Plan2 pl{};
-    static const int kch_e = env_int("FN_GRU2_KCH", 0), s_e = env_int("FN_GRU2_S", 0), wst_e = env_int("FN_GRU2_WST", 0);
+    const bool is_bwd = tag[0] == 'b';
+    static const int kch_f = env_int("FN_GRU2_KCH", 0), s_f = env_int("FN_GRU2_S", 0), wst_f = env_int("FN_GRU2_WST", 0);
+    static const int kch_b = env_int("FN_GRU2_KCH_BWD", 0), s_b = env_int("FN_GRU2_S_BWD", 0), wst_b = env_int("FN_GRU2_WST_BWD", 0);
+    const int kch_e = is_bwd ? kch_b : kch_f, s_e = is_bwd ? s_b : s_f, wst_e = is_bwd ? wst_b : wst_f;
     const int kch_env = kch_e ? kch_e : kch_dflt, s_env = s_e ? s_e : s_dflt, wst_env = wst_e ? wst_e : wst_dflt;
     int kch = kch_env == 1 || kch_env == 2 || kch_env == 4 ? kch_env : 2;
     while (kch > 1 && nkc % kch) kch >>= 1;
@@ -496,7 +782,7 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const cuuint
 }
 
 template <typename K>
-int launch2(K kernel, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t st) {
+int launch2(K kernel, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t st, int* fits = nullptr) {
     const void* fn = (const void*)kernel;
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
@@ -508,14 +794,15 @@ int launch2(K kernel, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t s
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[0].val.clusterDim.x = 2 * P.mc; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     attrs[1].id = cudaLaunchAttributeCooperative;           // every CTA must be co-resident: they wait on each other
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 2;
     int max_clusters = 0;
     FN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
-    FN_REQUIRE(max_clusters >= pairs, "fn_gru_seq_bf16: %d CTA pairs are not co-resident (max %d)", pairs, max_clusters);
+    if (fits) { *fits = max_clusters * P.mc >= pairs; if (!*fits) return FN_OK; }
+    FN_REQUIRE(max_clusters * P.mc >= pairs, "fn_gru_seq_bf16: %d CTA pairs are not co-resident (max %d)", pairs, max_clusters);
     void* args[] = {(void*)&P};
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {                                  // cooperative + cluster refused: residency was checked above
@@ -531,32 +818,99 @@ int launch2(K kernel, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t s
 // pairs; else UP = 64 (one chain per pair, H/64 pairs each) or UP = 32 with two chains per pair (FN_GRU2_GEO = 64 | 32).
 struct Geom { int up, cpp; };
 Geom pick_geo(int n, int H) {
-    static const int force = env_int("FN_GRU2_GEO", 64);
+    static const int force = env_int("FN_GRU2_GEO", 32);
     const int max_pairs = fn_num_sms() / 2;
     if (n * (H / 32) <= max_pairs) return {32, 1};
     if (force == 64 && n * (H / 64) <= max_pairs) return {64, 1};
     return {32, 2};
 }
 template <int UP>
-int launch_fwd(int kch, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t st) {
-    if (kch == 4) return launch2(gru2_fwd_kernel<UP, 4>, P, pairs, smem, st);
-    if (kch == 2) return launch2(gru2_fwd_kernel<UP, 2>, P, pairs, smem, st);
-    return launch2(gru2_fwd_kernel<UP, 1>, P, pairs, smem, st);
+int launch_fwd(int kch, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t st, int* fits) {
+    if (kch == 4) return launch2(gru2_fwd_kernel<UP, 4>, P, pairs, smem, st, fits);
+    if (kch == 2) return launch2(gru2_fwd_kernel<UP, 2>, P, pairs, smem, st, fits);
+    return launch2(gru2_fwd_kernel<UP, 1>, P, pairs, smem, st, fits);
+}
+
+int gru2_run_bwd(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes, cudaStream_t st) {
+    FN_REQUIRE(chains && n_chains > 0 && barrier_ws && ws_bytes >= (size_t)64 * n_chains, "fn_gru_seq_bf16: bad arguments");
+    FN_CHECK_CUDA(cudaMemsetAsync(barrier_ws, 0, (size_t)64 * n_chains, st));
+    const int nkc = 3 * H / 64, ppc = H / kUPB, max_pairs = fn_num_sms() / 2;
+    const Plan2 pl = plan2(nkc, kWChB, 1, 0, "bwd", 4, 3, 2);
+    FN_REQUIRE(pl.ok && pl.stages * pl.kch >= 4, "fn_gru_seq_bwd_bf16: no shared-memory plan for H=%d", H);   // (the ring doubles as the 64 KB staging area)
+    static const int mc_env = env_int("FN_GRU2_MC_BWD", 1);
+    int done = 0;
+    while (done < n_chains) {
+        int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc;
+        while (group * ppc > max_pairs) --group;
+        int mc = mc_env == 4 || mc_env == 2 ? mc_env : 1;
+        while (mc > 1 && (pl.kch % mc || ppc % mc)) mc >>= 1;
+        Tc2Launch P;
+        memset(&P, 0, sizeof(P));
+        auto encode_a = [&](int i, int mcv) {
+            const cuuint64_t dims[4] = {64, (cuuint64_t)B, (cuuint64_t)(4 * H / 64), (cuuint64_t)T};
+            const cuuint64_t str[3] = {(cuuint64_t)4 * H * 2, 128, (cuuint64_t)B * 4 * H * 2};
+            const cuuint32_t box[4] = {64, 128, (cuuint32_t)(pl.kch / mcv), 1};
+            return make_tmap_bf16_nd(&P.c[i].tmA, chains[done + i].dg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        };
+        for (int i = 0; i < group; ++i) {
+            const FnGruChainBf16& s = chains[done + i];
+            Tc2Chain& d = P.c[i];
+            FN_REQUIRE(s.hsx && s.w_hh_t && s.gates && s.dg && s.dh0, "fn_gru_seq_bwd_bf16: chain %d misses buffers", done + i);
+            int rc;
+            {   // W_hh^T [H][3H] as (k in chunk, unit, K chunk, -): one box = this CTA's 32 rows of KCH chunks
+                const cuuint64_t dims[4] = {64, (cuuint64_t)H, (cuuint64_t)nkc, 1};
+                const cuuint64_t str[3] = {(cuuint64_t)3 * H * 2, 128, (cuuint64_t)3 * H * H * 2};
+                const cuuint32_t box[4] = {64, 32, (cuuint32_t)pl.kch, 1};
+                if ((rc = make_tmap_bf16_nd(&d.tmW, s.w_hh_t, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+            }
+            if ((rc = encode_a(i, mc))) return rc;
+            {   // store of (dr, dz, dn, dn*r) of 64 units x 128 rows: (unit, row, gate, slab), one 64 KB box
+                const cuuint64_t dims[4] = {(cuuint64_t)H, (cuuint64_t)B, 4, (cuuint64_t)T};
+                const cuuint64_t str[3] = {(cuuint64_t)4 * H * 2, (cuuint64_t)H * 2, (cuuint64_t)B * 4 * H * 2};
+                const cuuint32_t box[4] = {64, 128, 4, 1};
+                if ((rc = make_tmap_bf16_nd(&d.tmS, s.dg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+            }
+            d.hsx = (__nv_bfloat16*)s.hsx; d.gates = (__nv_bfloat16*)s.gates;
+            d.dhs = s.dhs; d.dh_final = s.dh_final; d.dh_final_ld = s.dh_final_ld;
+            d.dg = (__nv_bfloat16*)s.dg; d.dh0 = s.dh0;
+            d.reverse = s.reverse; d.dhs_f32 = s.dhs_f32;
+        }
+        P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
+        P.n_chains = group; P.ppc = ppc; P.cpp = 1; P.B = B; P.T = T; P.H = H;
+        P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
+        P.dbg = nullptr;
+        P.mc = mc;
+        const int pairs = group * ppc;
+        int rc = FN_OK, fits = 0;
+        for (;;) {
+            rc = pl.kch == 4 ? launch2(gru2_bwd_kernel<4>, P, pairs, pl.smem, st, &fits)
+               : pl.kch == 2 ? launch2(gru2_bwd_kernel<2>, P, pairs, pl.smem, st, &fits) : launch2(gru2_bwd_kernel<1>, P, pairs, pl.smem, st, &fits);
+            if (rc != FN_OK || fits || P.mc == 1) break;
+            P.mc >>= 1;
+            for (int i = 0; i < group; ++i)
+                if ((rc = encode_a(i, P.mc))) return rc;
+        }
+        if (rc != FN_OK) return rc;
+        FN_REQUIRE(fits, "fn_gru_seq_bwd_bf16: %d CTA pairs are not co-resident", pairs);
+        done += group;
+    }
+    return FN_OK;
 }
 
 }  // namespace
 
 bool fn_gru2_eligible(bool bwd, int n_chains, int B, int H) {
-    static const int on = env_int("FN_GRU_V2", 1);
-    if (!on || (bwd && !(on & 2))) return false;
+    static const int on = env_int("FN_GRU_V2", 3);                 // bit 0: forward, bit 1: backward
+    if (!(on & (bwd ? 2 : 1))) return false;
     if (B <= 128 || B > 256 || H % 64 || H < 128) return false;
     if (H / 64 > fn_num_sms() / 2) return false;               // one chain must fit the machine
+    if (bwd) return plan2(3 * H / 64, kWChB, 1, 0, "bwd", 4, 3, 2).ok;
     return plan2(H / 64, Geo<32>::kWCh, 2, kStgAll, "fwd").ok;
 }
 
 int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
                 cudaStream_t st) {
-    FN_REQUIRE(!bwd, "fn_gru2_run: backward not built yet");
+    if (bwd) return gru2_run_bwd(chains, n_chains, B, T, H, barrier_ws, ws_bytes, st);
     FN_REQUIRE(chains && n_chains > 0 && barrier_ws && ws_bytes >= (size_t)64 * n_chains, "fn_gru_seq_bf16: bad arguments");
     FN_CHECK_CUDA(cudaMemsetAsync(barrier_ws, 0, (size_t)64 * n_chains, st));
     const int nkc = H / 64, max_pairs = fn_num_sms() / 2;
@@ -569,6 +923,12 @@ int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int
         // ring defaults from the config-3 sweeps: N = 96 wants 64 KB state boxes (everything streamed), N = 192 32 KB boxes
         const Plan2 pl = g.up == 64 ? plan2(nkc, w_chunk, cpp, kStgAll, "fwd64", 2, 3, 2) : plan2(nkc, w_chunk, cpp, kStgAll, "fwd32", 4, 2, 2);
         FN_REQUIRE(pl.ok, "fn_gru_seq_bf16: no shared-memory plan for H=%d", H);
+        // Pairs per cluster: the same-rank CTAs of a cluster need the same state slab, so each loads 1/mc of every stage and
+        // multicasts it -- L2 reads of the state (the bulk of the step's traffic; the kernels are bound by the ~6 kB/clk the L2
+        // delivers to the SMs) drop by mc.  Largest of 4, 2, 1 that divides the stage and the pairs of a chain and is co-resident.
+        static const int mc_env = env_int("FN_GRU2_MC", 4);
+        int mc = mc_env == 4 || mc_env == 2 ? mc_env : 1;
+        while (mc > 1 && (pl.kch % mc || ppc % mc)) mc >>= 1;
         Tc2Launch P;
         memset(&P, 0, sizeof(P));
         for (int i = 0; i < group; ++i) {
@@ -587,7 +947,7 @@ int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int
             {   // hsx [T+1][B][H] as (k in chunk, row, K chunk, slab): one box = 128 rows of KCH chunks (KCH x 16 KB)
                 const cuuint64_t dims[4] = {64, (cuuint64_t)B, (cuuint64_t)nkc, (cuuint64_t)T + 1};
                 const cuuint64_t str[3] = {(cuuint64_t)H * 2, 128, (cuuint64_t)B * H * 2};
-                const cuuint32_t box[4] = {64, 128, (cuuint32_t)pl.kch, 1};
+                const cuuint32_t box[4] = {64, 128, (cuuint32_t)(pl.kch / mc), 1};
                 if ((rc = make_tmap_bf16_nd(&d.tmA, s.hsx, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
             }
             {   // store of the new state tile: (unit, row, slab), box 32 units x 128 rows (64-byte rows)
@@ -607,8 +967,21 @@ int fn_gru2_run(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
         P.dbg = fn_gru_dbg_ptr();
         const int pairs = ((group + cpp - 1) / cpp) * ppc;
-        const int rc = g.up == 64 ? launch_fwd<64>(pl.kch, P, pairs, pl.smem, st) : launch_fwd<32>(pl.kch, P, pairs, pl.smem, st);
+        P.mc = mc;
+        int rc = FN_OK, fits = 0;
+        for (;;) {                                               // (the state boxes above were sized for `mc`: re-encode when it shrinks)
+            rc = g.up == 64 ? launch_fwd<64>(pl.kch, P, pairs, pl.smem, st, &fits) : launch_fwd<32>(pl.kch, P, pairs, pl.smem, st, &fits);
+            if (rc != FN_OK || fits || P.mc == 1) break;
+            P.mc >>= 1;
+            for (int i = 0; i < group; ++i) {
+                const cuuint64_t dims[4] = {64, (cuuint64_t)B, (cuuint64_t)nkc, (cuuint64_t)T + 1};
+                const cuuint64_t str[3] = {(cuuint64_t)H * 2, 128, (cuuint64_t)B * H * 2};
+                const cuuint32_t box[4] = {64, 128, (cuuint32_t)(pl.kch / P.mc), 1};
+                if ((rc = make_tmap_bf16_nd(&P.c[i].tmA, chains[done + i].hsx, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+            }
+        }
         if (rc != FN_OK) return rc;
+        FN_REQUIRE(fits, "fn_gru_seq_bf16: %d CTA pairs are not co-resident", pairs);
         done += group;
     }
     return FN_OK;

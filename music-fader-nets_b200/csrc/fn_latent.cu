@@ -5,6 +5,9 @@
 #include "fn_common.cuh"
 
 namespace {
+// supervised component label, clamped to [0, K) (the host mirror counts out-of-range labels and raises)
+__device__ __forceinline__ int fn_label(long long y, int K) { return y < 0 ? 0 : y >= K ? K - 1 : (int)y; }
+
 
 constexpr float kLn2Pi = 1.8378770664093453f;
 constexpr int kMaxK = 32;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(1024) gm_kl_fwd_kernel(const float* __restrict
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int b = w; b < B; b += 32) {
         const float* q = qy + (long long)b * K;
-        const int k_lo = mode ? (int)ylab[b] : 0, k_hi = mode ? k_lo + 1 : K;
+        const int k_lo = mode ? fn_label(ylab[b], K) : 0, k_hi = mode ? k_lo + 1 : K;
         for (int k = k_lo; k < k_hi; ++k) {
             float s = 0.f;
             for (int d = lane; d < Z; d += 32) {
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(1024) gm_kl_fwd_kernel(const float* __restrict
             float mx = -INFINITY, den = 0.f;
             for (int k = 0; k < K; ++k) mx = fmaxf(mx, q[k]);
             for (int k = 0; k < K; ++k) den += expf(q[k] - mx);
-            a2 += (mx + logf(den)) - q[(int)ylab[b]];
+            a2 += (mx + logf(den)) - q[fn_label(ylab[b], K)];
         }
     }
     if (lane == 0) { acc[0][w] = a0; acc[1][w] = a1; acc[2][w] = a2; }
@@ -160,7 +163,7 @@ __global__ void gm_kl_bwd_rows_kernel(const float* __restrict__ mu, const float*
     if (b >= B) return;
     const float d0 = dout3[0] / (float)B, d1 = dout3[1] / (float)B, d2 = dout3[2] / (float)B;
     const float* q = qy + (long long)b * K;
-    const int k_lo = mode ? (int)ylab[b] : 0, k_hi = mode ? k_lo + 1 : K;
+    const int k_lo = mode ? fn_label(ylab[b], K) : 0, k_hi = mode ? k_lo + 1 : K;
     // per-dim grads
     for (int d = lane; d < Z; d += 32) {
         const float m = mu[(long long)b * Z + d], sq = sc[(long long)b * Z + d];
@@ -202,7 +205,7 @@ __global__ void gm_kl_bwd_rows_kernel(const float* __restrict__ mu, const float*
             gq = d0 * s + d1 * lk / (float)K;
             gl = d1 / (float)K * (q[k] - expf(lk) * sumq);
         } else {
-            gq = d2 * (expf(q[k] - mxq) / denq - (k == (int)ylab[b] ? 1.f : 0.f));
+            gq = d2 * (expf(q[k] - mxq) / denq - (k == fn_label(ylab[b], K) ? 1.f : 0.f));
         }
         if (lane == 0) {
             dqy[(long long)b * K + k] = gq;
@@ -221,7 +224,7 @@ __global__ void gm_kl_bwd_lookup_kernel(const float* __restrict__ mu, const floa
     const float d0 = dout3[0] / ((float)B * (float)Z);
     float g = 0.f;
     for (long long b = 0; b < B; ++b) {
-        const float wgt = mode ? ((int)ylab[b] == k ? 1.f : 0.f) : qy[b * K + k];
+        const float wgt = mode ? (fn_label(ylab[b], K) == k ? 1.f : 0.f) : qy[b * K + k];
         g -= wgt * (mu[b * Z + d] - m) * ip2;
     }
     dmul[i] = g * d0;
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) gm_kl_fwd_fast_kernel(const fl
         // per-row scalars fetched with the row, before any arithmetic (a load in the middle of the dependent chain costs
         // a memory round trip per row)
         float q[KA], l[KA];
-        const int yl = mode ? (int)ylab[b] : -1;
+        const int yl = mode ? fn_label(ylab[b], K) : -1;
 #pragma unroll
         for (int k = 0; k < (KT > 0 ? KT : K); ++k) { q[k] = __ldg(qy + b * K + k); l[k] = mode == 0 ? __ldg(ll + b * K + k) : 0.f; }
         float kl[KA];
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(kRowThreads, 3) gm_kl_bwd_rows_fast_kernel(
         float4 mr[NJ], sr[NJ];
         load_chunks<LPR, NJ>(mu, b, Z, sl, mr); load_chunks<LPR, NJ>(sc, b, Z, sl, sr);
         float q[KA], l[KA];
-        const int yl = mode ? (int)ylab[b] : -1;
+        const int yl = mode ? fn_label(ylab[b], K) : -1;
 #pragma unroll
         for (int k = 0; k < (KT > 0 ? KT : K); ++k) { q[k] = __ldg(qy + b * K + k); l[k] = mode == 0 ? __ldg(ll + b * K + k) : 0.f; }
         // per-dimension gradients
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(256) lookup_grad_stage1_kernel(const float* __
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         for (long long b = r0 + grp; b < r1; b += 4) {
             float wgt;
-            if (WHICH == 0) wgt = mode ? ((int)ylab[b] == k ? 1.f : 0.f) : qy[b * K + k];
+            if (WHICH == 0) wgt = mode ? (fn_label(ylab[b], K) == k ? 1.f : 0.f) : qy[b * K + k];
             else wgt = qy_dl(qy, dll, dqy, b, K, k);
             const float4 v = ld4(x + b * Z + d);
             g.x += wgt * (v.x - m.x); g.y += wgt * (v.y - m.y); g.z += wgt * (v.z - m.z); g.w += wgt * (v.w - m.w);

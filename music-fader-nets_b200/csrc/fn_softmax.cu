@@ -56,7 +56,7 @@ __global__ void vocab_lsm_fwd_kernel(const float* __restrict__ logits, const int
         }
     }
     if (MODE == 1 && lane == 0) {
-        const int tg = (int)target[(long long)b * T + t];
+        const int tg = (int)min((long long)V - 1, max(0LL, (long long)target[(long long)b * T + t]));
         lse_tm[row] = lse;
         loss_rows[row] = lse - x[tg];
     }
@@ -102,7 +102,7 @@ __global__ void vocab_nll_bwd_kernel(const float* __restrict__ logits, const flo
     const int t = (int)(row / B), b = (int)(row % B);
     const float sc = (scale_dev ? *scale_dev : 1.f) * scale_host;
     const float lse = lse_tm[row];
-    const int tg = (int)target[(long long)b * T + t];
+    const int tg = (int)min((long long)V - 1, max(0LL, (long long)target[(long long)b * T + t]));
     const float* x = logits + row * V;
     float* d = dlogits + row * V;
     if (NV > 0) {
@@ -168,7 +168,10 @@ __global__ void reduce_stage1(const float* __restrict__ x, const int64_t* __rest
     double s = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if (GATHER == 0) s += (double)x[i];
-        else s -= (double)x[i * C + target[i]];
+        else {
+            const long long tg = target[i];
+            s -= (double)x[i * C + (tg < 0 ? 0 : tg >= C ? C - 1 : tg)];      // clamped: never out of bounds (ops.check_index counts + raises)
+        }
     }
     s = fn_block_sum_d(s, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
@@ -215,7 +218,8 @@ __global__ void nll_bwd_kernel(const int64_t* __restrict__ target, long long row
                                float* __restrict__ dlogp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
-    dlogp[i * C + target[i]] += -dloss[0] / (float)rows;
+    const long long tg = target[i];
+    dlogp[i * C + (tg < 0 ? 0 : tg >= C ? C - 1 : tg)] += -dloss[0] / (float)rows;
 }
 
 int red_blocks(long long n) { return (int)max(1LL, min((long long)kRedBlocks, (n + 1023) / 1024)); }

@@ -207,10 +207,23 @@ __device__ __forceinline__ void tma_load_4d_2cta_u32(uint32_t smem_dst, const CU
         ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// multicast form: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and the bytes complete on the
+// barrier at `bar`'s CTA-relative offset in the LEADER of each destination CTA's pair
+__device__ __forceinline__ void tma_load_4d_2cta_mc_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                        uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
 // ---- TMA store (shared -> global), bulk-group completion --------------------------------------------------
 __device__ __forceinline__ void tma_store_3d_u32(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(m), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_u32(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(m), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>

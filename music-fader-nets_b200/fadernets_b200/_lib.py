@@ -69,6 +69,8 @@ _SIGNATURES = {
     "fn_ids_to_onehot": (I, [V, I, I, I, V, V]),
     "fn_ids_to_time_major": (I, [V, I, I, I, I, V, V]),
     "fn_transpose_f32": (I, [V, LL, V, LL, I, I, I, V]),
+    "fn_check_index_i64": (I, [V, LL, LL, V, V]),
+    "fn_clamp_index_i32": (I, [V, LL, I, V, V]),
     "fn_clean_tokens": (I, [V, I, I, V, V, V]),
     "fn_add_f32": (I, [V, V, LL, V]),
     "fn_emb_grad_scratch_bytes": (SZ, [I, I, I, I]),

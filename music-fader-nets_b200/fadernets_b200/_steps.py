@@ -77,5 +77,13 @@ def optimise(model, optimizer, loss):
 
 
 def to_floats(*scalars):
-    """One device->host transfer instead of the reference's 8 `.item()` syncs."""
-    return tuple(torch.stack([s.reshape(()) for s in scalars]).tolist())
+    """One device->host transfer instead of the reference's 8 `.item()` syncs (+ the index-range verdict of this step)."""
+    from . import ops
+    vals = torch.stack([s.reshape(()) for s in scalars])
+    bad = ops._bad_counter(vals.device)
+    out = torch.cat([vals.float(), bad.float()]).tolist()
+    if out[-1]:
+        bad.zero_()
+        raise IndexError(f"fadernets_b200: {int(out[-1])} token / target / label index(es) out of range "
+                         "(the reference's nll_loss / Embedding raise here too)")
+    return tuple(out[:-1])

@@ -147,13 +147,14 @@ class _FaderBase(nn.Module):
             buf = torch.empty((T + 1, B), dtype=torch.int32, device=dev)
             xi = x.long().contiguous()
             ops.LIB.call("fn_ids_to_time_major", ops._p(xi), B, T, 0, 0, ops._p(buf, B), ops.stream_ptr(dev))
+            ops.clamp_index(buf[1:], V)                 # nn.Embedding / one-hot scatter of the reference raise on a bad id
         buf[0].fill_(V - START_TOKEN_FROM_END)
         return buf
 
     def _attr_ids(self, a: torch.Tensor, dims: int):
         if a.dim() == 3:
             return ops.onehot_to_ids_tm(a)
-        return ops.ids_to_tm(a)
+        return ops.ids_to_tm(a, dims=dims)
 
     def _draw_eps(self, B, Z, dev):
         """Noise for the reparameterisation (gmm_model.py:229-235): the reference samples on the CPU

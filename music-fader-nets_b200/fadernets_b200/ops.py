@@ -50,6 +50,46 @@ def _reduce_scratch(dev):
 
 
 # ------------------------------------------------------------------------------------------------
+# index validation
+# ------------------------------------------------------------------------------------------------
+# The reference's F.nll_loss / nn.Embedding raise on an out-of-range index.  Here every consuming kernel clamps (no
+# out-of-bounds access), offending entries are COUNTED on the device, and the mirror raises IndexError at its next
+# synchronisation point (train / evaluate read their results back there; `raise_on_bad_index()` for other callers).
+_BAD_INDEX = {}
+
+
+def _bad_counter(dev) -> torch.Tensor:
+    key = torch.device(dev).index or 0
+    t = _BAD_INDEX.get(key)
+    if t is None:
+        t = _BAD_INDEX[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t
+
+
+def check_index(idx: torch.Tensor, hi: int):
+    """Count entries of the int64 tensor `idx` outside [0, hi) (targets / labels; consumers clamp)."""
+    idx = idx if idx.is_contiguous() else idx.contiguous()
+    LIB.call("fn_check_index_i64", _p(idx), idx.numel(), hi, _p(_bad_counter(idx.device)), _st(idx))
+
+
+def clamp_index(idx: torch.Tensor, hi: int):
+    """Clamp the int32 id buffer `idx` into [0, hi) in place and count what had to be clamped."""
+    LIB.call("fn_clamp_index_i32", _p(idx), idx.numel(), hi, _p(_bad_counter(idx.device)), _st(idx))
+
+
+def raise_on_bad_index(dev=None):
+    """Synchronises; raises IndexError if any index checked since the last call was out of range."""
+    for key, t in list(_BAD_INDEX.items()):
+        if dev is not None and (torch.device(dev).index or 0) != key:
+            continue
+        n = int(t.item())
+        if n:
+            t.zero_()
+            raise IndexError(f"fadernets_b200: {n} token / target / label index(es) out of range "
+                             "(the reference's nll_loss / Embedding raise here too)")
+
+
+# ------------------------------------------------------------------------------------------------
 # token plumbing (no autograd)
 # ------------------------------------------------------------------------------------------------
 def onehot_to_ids_tm(onehot: torch.Tensor) -> torch.Tensor:
@@ -74,13 +114,16 @@ def ids_to_onehot(ids: torch.Tensor, dims: int) -> torch.Tensor:
     return out if ids.dim() > 1 else out.view(B, dims)
 
 
-def ids_to_tm(ids: torch.Tensor, shift: int = 0, start_token: int = 0) -> torch.Tensor:
-    """int64 (B,T) -> int32 [T,B]; shift=1 prepends the start token (teacher-forced decoder input)."""
+def ids_to_tm(ids: torch.Tensor, shift: int = 0, start_token: int = 0, dims: Optional[int] = None) -> torch.Tensor:
+    """int64 (B,T) -> int32 [T,B]; shift=1 prepends the start token (teacher-forced decoder input).
+    `dims`: vocabulary size -- ids are validated (clamped + counted, see check_index)."""
     require_cuda(ids)
     ids = ids.long().contiguous()
     B, T = ids.shape
     out = torch.empty((T, B), dtype=torch.int32, device=ids.device)
     LIB.call("fn_ids_to_time_major", _p(ids), B, T, shift, start_token, _p(out), _st(out))
+    if dims is not None:
+        clamp_index(out, dims)
     return out
 
 
@@ -410,6 +453,7 @@ class NllMeanFn(torch.autograd.Function):
         Cc = logp.shape[-1]
         rows = logp.numel() // Cc
         target = target.long().contiguous()
+        check_index(target, Cc)
         loss = torch.empty((), dtype=F32, device=logp.device)
         scratch, n = _reduce_scratch(logp.device)
         LIB.call("fn_nll_mean_fwd", _p(logp), _p(target), rows, Cc, _p(loss), _p(scratch), n, _st(loss))
@@ -519,6 +563,7 @@ class GmKlFn(torch.autograd.Function):
         K = mu_lookup.shape[0]
         if y_label is not None:
             y_label = y_label.long().contiguous()
+            check_index(y_label, K)
         out = torch.empty(3, dtype=F32, device=mu.device)
         ws, nb = _latent_scratch(B, Z, K, mu.device)
         LIB.call("fn_gm_kl_fwd", _p(mu), _p(scale), _p(mu_lookup), _p(logvar_lookup), _p(qy), _p(ll), _p(y_label),

@@ -431,3 +431,30 @@ def test_tc_gemm_splitk(dev, a_mn, b_mn, c_bf16):
     assert torch.equal(outs[0], outs[1]), "split-K result is not run-to-run deterministic"
     ref = (C0.to(bf).double() if c_bf16 else C0.double()) + A.double() @ Bm.double() + bias.double()
     close(outs[0], ref, rtol=1e-2 if c_bf16 else 2e-5, atol=5e-2 if c_bf16 else 2e-3, what="split-K gemm")
+
+
+def test_index_validation(dev):
+    """Out-of-range token / target / label indices: the reference raises (F.nll_loss, nn.Embedding); here they are clamped
+    on the device (no out-of-bounds access), counted, and raised as IndexError at the next synchronisation."""
+    from fadernets_b200 import ops
+    ops.raise_on_bad_index()                                   # clear
+    ids = torch.tensor([[0, 5, 341, 7], [1, 2, 3, 4]], device=dev)
+    tm = ops.ids_to_tm(ids, dims=342)
+    ops.raise_on_bad_index()
+    assert tm.t().tolist() == ids.tolist()
+    bad = ids.clone(); bad[0, 1] = 999; bad[1, 3] = -3
+    tm = ops.ids_to_tm(bad, dims=342)
+    assert tm.t().tolist() == [[0, 341, 341, 7], [1, 2, 3, 0]]
+    with pytest.raises(IndexError):
+        ops.raise_on_bad_index()
+    ops.raise_on_bad_index()                                   # the counter was reset
+    logp = torch.log_softmax(rnd(6, 5, seed=1, dev=dev), -1).requires_grad_(True)
+    tgt = torch.tensor([0, 4, 2, 7, 1, -1], device=dev)
+    loss = ops.NllMeanFn.apply(logp, tgt)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(logp.grad).all()
+    with pytest.raises(IndexError):
+        ops.raise_on_bad_index()
+    # a one-hot row without a maximum still yields a valid id
+    oh = torch.full((1, 2, 4), float("nan"), device=dev)
+    assert ops.onehot_to_ids_tm(oh).flatten().tolist() == [0, 0]
