@@ -322,7 +322,14 @@ class GruGroupBf16Fn(torch.autograd.Function):
 # decoder stack: sub-decoder r, sub-decoder n, global cell 1 and global cell 2 as one wavefront
 # ------------------------------------------------------------------------------------------------
 def _segments(T: int):
-    """Time segments of the wavefront: cell 2 runs one segment behind cell 1 in the same launch."""
+    """Time segments of the wavefront: cell 2 runs one segment behind cell 1 in the same launch.  S segments cost
+    T (S + 1) / S chain steps instead of 2 T; more segments = fewer idle steps in the head / tail launches but more
+    launches (FN_WAVEFRONT_SEGMENTS, default 16 where T allows: config 3 measured 43.0 / 42.2 / 42.0 ms per step at 4 / 8 / 16)."""
+    import os
+    want = int(os.environ.get("FN_WAVEFRONT_SEGMENTS", "16"))
+    for S in (16, 8):
+        if want >= S and T % S == 0 and T // S >= 32:
+            return S
     if T % 4 == 0 and T >= 64:
         return 4
     if T % 2 == 0 and T >= 16:
