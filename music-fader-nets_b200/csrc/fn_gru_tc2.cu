@@ -96,7 +96,8 @@ __device__ __forceinline__ void publish2(unsigned* ctr) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
 #endif
 }
-constexpr int kBarStage = 2;
+constexpr int kBarStage = 2;                   // named barriers 2, 3: epilogue warps (arrive) -> store warp (sync), per chain of the pair
+constexpr int kBarPub = 4;                     // named barriers 4, 5: store warp (arrive, after the publish) -> epilogue warps (sync)
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 #define FN_STAMP2(i, k)                                                         \
     do {                                                                        \
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                     publish2(P.bar + (ch0 + k) * 16 + rank);
                 }
                 __syncwarp();
+                asm volatile("bar.arrive %0, %1;" ::"r"(kBarPub + k), "n"((kEW2 + 1) * 32) : "memory");   // the epilogue's bulk stores may go now
                 FN_STAMP2(s, k * 32 + 10);
             }
         }
@@ -432,6 +434,10 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                 tc::fence_proxy_async();
                 if (P.dbg != nullptr && blockIdx.x == 0 && lane == 0) P.dbg[(long long)s * 64 + k * 32 + 12 + (warp - kEpi0)] = clk();
                 asm volatile("bar.arrive %0, %1;" ::"r"(kBarStage + k), "n"((kEW2 + 1) * 32) : "memory");
+                // The saved gates (and the next step's input gather) are off the critical path, but they share the SM's
+                // load/store pipe with the hand-over: issued now, 64 store instructions per CTA queue ahead of the store
+                // warp's counter update and the loader's polls (measured: +1.5k cycles per step).  Wait for the publish.
+                asm volatile("bar.sync %0, %1;" ::"r"(kBarPub + k), "n"((kEW2 + 1) * 32) : "memory");
                 if (row_ok) {
                     if (c.gates) {                             // off the critical path
                         stb<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), r);
@@ -627,6 +633,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_bwd_kernel(const __grid_con
                 publish2(gflag);
             }
             __syncwarp();
+            asm volatile("bar.arrive %0, %1;" ::"n"(kBarPub), "n"((kEW2 + 1) * 32) : "memory");
         }
     } else {
         // ------------------------------- gate-gradient epilogue (16 warps) --------------------------------------
@@ -644,7 +651,9 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_bwd_kernel(const __grid_con
             const int s = T - 1 - i;
             const int tau = c.reverse ? T - 1 - s : s;
             const long long row = (long long)tau * B + b;
-            // ---- saved forward values and incoming gradients: fetch before waiting for the MMAs
+            // ---- saved forward values and incoming gradients: fetch before waiting for the MMAs -- but after the previous
+            // iteration's hand-over (these 6 x 16 warps of loads would queue ahead of the publish and the loader's polls)
+            if (i > 0) asm volatile("bar.sync %0, %1;" ::"n"(kBarPub), "n"((kEW2 + 1) * 32) : "memory");
             uint32_t wr[UT / 2], wz[UT / 2], wn[UT / 2], wg[UT / 2], wh[UT / 2];
             float din[UT];
 #pragma unroll
