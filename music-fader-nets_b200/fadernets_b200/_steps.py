@@ -63,12 +63,16 @@ def latent_reg(z_out, r, n):
     """trainer_gmm.py:199-217 / trainer.py:117-132 (Pati et al. 2019), latent dim 0 only."""
     z_r, z_n = z_out
     dev = z_r.device
+    from . import parallel
+    if parallel.global_latent_reg_enabled():           # pairs over the GLOBAL batch (one small all-gather per latent)
+        return parallel.LatentRegGlobalFn.apply(z_r, _attr(r, dev)), parallel.LatentRegGlobalFn.apply(z_n, _attr(n, dev))
     return LatentRegFn.apply(z_r, _attr(r, dev)), LatentRegFn.apply(z_n, _attr(n, dev))
 
 
 def optimise(model, optimizer, loss):
     """loss.backward(); clip_grad_norm_(params, 1); optimizer.step()  (trainer_gmm.py:249-251)."""
-    loss.backward()
+    scale = getattr(getattr(optimizer, "grad_sync", None), "loss_scale", 1.0)
+    (loss if scale == 1.0 else loss * scale).backward()        # data parallel: the 1/world of the gradient mean, folded into backward
     if isinstance(optimizer, FusedAdam):
         optimizer.step()                       # global-norm clip (max_norm=1) is fused into the update
     else:

@@ -65,13 +65,21 @@ class _FaderBase(nn.Module):
 
     # ---------------------------------------------------------------- flat parameter storage
     def live_parameters(self):
-        return [(n, p) for n, p in self.named_parameters() if p.requires_grad and not n.startswith(DEAD_PREFIXES)]
+        """Parameters that receive gradients, in flat-buffer order: decoder-side first, the encoders last, so that the
+        data-parallel gradient buckets are contiguous ranges (parallel.decoder_first)."""
+        from .parallel import decoder_first
+        return decoder_first([(n, p) for n, p in self.named_parameters() if p.requires_grad and not n.startswith(DEAD_PREFIXES)])
 
     def _flat_ok(self):
         if self._flat is None:
             return False
-        n, p = self.live_parameters()[0]
-        return p.data_ptr() == self._flat.data_ptr() and p.device == self._flat.device
+        off = 0
+        base = self._flat.data_ptr()
+        for _, p in self.live_parameters():              # every live parameter must still be a view of the flat buffer
+            if p.data_ptr() != base + off * 4 or p.device != self._flat.device:
+                return False
+            off += ((p.numel() + 3) // 4) * 4
+        return True
 
     def flatten_parameters_(self):
         """Packs the live parameters (and their grads) into two flat fp32 buffers so the
@@ -81,7 +89,7 @@ class _FaderBase(nn.Module):
         live = self.live_parameters()
         dev = live[0][1].device
         total = sum(((p.numel() + 3) // 4) * 4 for _, p in live)
-        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
         grad = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
         with torch.no_grad():

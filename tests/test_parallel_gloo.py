@@ -30,9 +30,29 @@ def _worker(rank, world, port, q):
     s = float(sum(p.double().sum() for p in m.state_dict().values()))
     sums = [None] * world
     dist.all_gather_object(sums, s)
+    # overlapped, bucketed all-reduce: bucket 0 (decoder-side parameters) goes out from the post-accumulate hooks while
+    # backward is still running, bucket 1 (the encoders) in step(); SUM collectives + 1/world folded into the loss
+    flat, grad = m.flatten_parameters_()
+    ov = parallel.OverlappedGradAllReduce(m)
+    names = [n for n, _ in m.live_parameters()]
+    first_enc = min(i for i, n in enumerate(names) if n.startswith(parallel.ENCODER_PREFIXES))
+    ok_order = all(n.startswith(parallel.ENCODER_PREFIXES) for n in names[first_enc:]) and 0 < ov.split < grad.numel()
+    grad.zero_()
+    loss = sum(((rank + 1) * (i + 1)) * p.sum() for i, (_, p) in enumerate(m.live_parameters()))
+    (loss * ov.loss_scale).backward()
+    issued_early = ov._handle is not None                      # bucket 0 was issued from the hooks, before the sync call
+    ov(grad)
+    expect = torch.cat([torch.full((((p.numel() + 3) // 4) * 4,), (i + 1) * (1 + 2) / 2.0) * torch.cat(
+        [torch.ones(p.numel()), torch.zeros(((p.numel() + 3) // 4) * 4 - p.numel())]) for i, (_, p) in enumerate(m.live_parameters())])
+    ok_overlap = ok_order and issued_early and torch.allclose(grad, expect) and ov.calls == 1
+    # second step re-arms the hooks
+    grad.zero_()
+    (loss * ov.loss_scale).backward() if False else (sum(p.sum() for _, p in m.live_parameters()) * ov.loss_scale).backward()
+    ov(grad)
+    ok_overlap = ok_overlap and ov.calls == 2 and bool((grad[:5] == 1.0).all())
     # shards tile the batch
     lo, hi = parallel.shard_bounds(11, rank, world)
-    q.put((rank, ok_mean, sums, (lo, hi), hook.calls))
+    q.put((rank, ok_mean and ok_overlap, sums, (lo, hi), hook.calls))
     dist.destroy_process_group()
 
 
