@@ -68,12 +68,15 @@ def gru_flops_per_token(H):
 
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the GRU kernel launches of one step, from the committed
-    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None if it was not captured."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        return json.load(open(path)).get(workload)
-    except Exception:
-        return None
+    `ncu --set full` capture of this workload (profiles/r02_traffic.json, else r01); None if it was not captured."""
+    for tag in ("r02", "r01"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"))).get(workload)
+        except Exception:
+            v = None
+        if v is not None:
+            return v
+    return None
 
 
 def measured_peaks():
@@ -271,7 +274,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": 8 * 4, "ms_per_step": round(sec_e2e / args.steps * 1e3, 3)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": ("gru_tc_kernel fwd+bwd (persistent tcgen05 recurrent GEMM + gates)" if prec == "bf16" else
+        "roofline": {"kernel": ("gru2_fwd_kernel + gru2_bwd_kernel (persistent tcgen05 cta_group::2 recurrent GEMM + gates, CTA pairs)" if prec == "bf16" else
                                 "gru_fwd_kernel + gru_bwd_kernel (persistent fp32 SIMT recurrent GEMM + gates)"),
                      "bound": "tensor", "achieved": round(achieved, 3) if achieved else None,
                      "peak": peaks["tf_sust"], "unit": "TFLOP/s",

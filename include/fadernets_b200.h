@@ -37,6 +37,9 @@ extern "C" {
 
 const char* fn_last_error(void);
 int fn_abi_version(void);
+/* sha256 prefix of the sources this binary was built from (__graft_entry__.source_hash()); the Python binding refuses a
+ * library whose hash differs from the sources it ships with. */
+const char* fn_source_hash(void);
 /* sm count / compute capability of the current device (host out-params). */
 int fn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
 
@@ -183,6 +186,15 @@ int fn_decode_greedy_bf16(const void* w_hh1, const float* b_hh1, const void* emb
 /* Profiling aid: CTA 0 of the following fn_gru_seq_*_bf16 launches writes clock64 stamps of its pipeline
  * events into `device_buffer` ((T+1)*2*16 int64); NULL switches it off. */
 int fn_gru_debug_timeline(void* device_buffer);
+
+/* Element-wise pieces of the sibling models built on the same blocks: MusicAttrFaderNets' discriminator
+ * heads `dropout(relu(linear(reverse(z))))` (model_v2.py:426-435, 574-575: relu x keep-mask/(1-p); the gradient reversal
+ * is fn_scale_f32 with alpha = -1 in backward) and the adversarial MSE of trainer_fader.py:105-110 (mean over the batch). */
+int fn_relu_mask_fwd(const float* x, const float* mask, float* y, long long n, void* stream);
+int fn_relu_mask_bwd(const float* x, const float* mask, const float* dy, float* dx, long long n, void* stream);
+int fn_scale_f32(const float* src, float* dst, float alpha, long long n, void* stream);
+int fn_mse_mean_fwd(const float* x, const float* y, long long n, float* loss, void* stream);
+int fn_mse_mean_bwd(const float* x, const float* y, long long n, const float* dloss, float* dx, void* stream);
 
 /* Index validation.  The reference's F.nll_loss / nn.Embedding / Embedding lookups (trainer_gmm.py:131-136,156,182;
  * gmm_model.py:84,109,132) raise on an out-of-range index.  Here every kernel that consumes an index CLAMPS it (no

@@ -14,6 +14,10 @@ void fn_set_error(const char* fmt, ...) {
 }
 extern "C" const char* fn_last_error(void) { return g_err; }
 extern "C" int fn_abi_version(void) { return FN_ABI_VERSION; }
+#ifndef FN_SOURCE_HASH
+#define FN_SOURCE_HASH "unknown"
+#endif
+extern "C" const char* fn_source_hash(void) { return FN_SOURCE_HASH; }
 
 static int g_attr_dev = -1, g_sms = 0, g_smem = 0;
 static void refresh_attrs() {
@@ -99,6 +103,35 @@ __global__ void clamp_index_i32_kernel(int32_t* __restrict__ idx, long long n, i
     if (__syncthreads_or(c)) {
         if (c) atomicAdd(bad, c);
     }
+}
+
+// ---- small element-wise pieces of the sibling models (MusicAttrFaderNets, model_v2.py:426-435, 574-575; trainer_fader.py:105-110)
+// y = relu(x) * mask   (mask = the dropout keep mask already divided by 1 - p, or NULL)
+__global__ void relu_mask_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fmaxf(x[i], 0.f) * (mask ? mask[i] : 1.f);
+}
+__global__ void relu_mask_bwd_kernel(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ dy,
+                                     float* __restrict__ dx, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dx[i] = x[i] > 0.f ? dy[i] * (mask ? mask[i] : 1.f) : 0.f;
+}
+__global__ void scale_kernel(const float* __restrict__ src, float* __restrict__ dst, float alpha, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = alpha * src[i];
+}
+// loss = mean_i (x_i - y_i)^2 : ONE block, fixed summation order (deterministic); n is a batch size
+__global__ void mse_mean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ loss) {
+    __shared__ double red[33];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) { const double d = (double)x[i] - (double)y[i]; s += d * d; }
+    s = fn_block_sum_d(s, red);
+    if (threadIdx.x == 0) loss[0] = (float)(s / (double)n);
+}
+__global__ void mse_mean_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, const float* __restrict__ dloss,
+                                    float* __restrict__ dx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dx[i] = 2.f * (x[i] - y[i]) / (float)n * dloss[0];
 }
 
 __global__ void transpose_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
@@ -302,6 +335,37 @@ extern "C" int fn_clamp_index_i32(int32_t* idx, long long n, int hi, int32_t* ba
     if (n == 0) return FN_OK;
     const int blocks = (int)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
     clamp_index_i32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, n, hi, bad_count);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+
+extern "C" int fn_relu_mask_fwd(const float* x, const float* mask, float* y, long long n, void* stream) {
+    FN_REQUIRE(x && y && n >= 0, "fn_relu_mask_fwd: bad args");
+    if (n) relu_mask_fwd_kernel<<<fn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, y, n);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+extern "C" int fn_relu_mask_bwd(const float* x, const float* mask, const float* dy, float* dx, long long n, void* stream) {
+    FN_REQUIRE(x && dy && dx && n >= 0, "fn_relu_mask_bwd: bad args");
+    if (n) relu_mask_bwd_kernel<<<fn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, dy, dx, n);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+extern "C" int fn_scale_f32(const float* src, float* dst, float alpha, long long n, void* stream) {
+    FN_REQUIRE(src && dst && n >= 0, "fn_scale_f32: bad args");
+    if (n) scale_kernel<<<fn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, alpha, n);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+extern "C" int fn_mse_mean_fwd(const float* x, const float* y, long long n, float* loss, void* stream) {
+    FN_REQUIRE(x && y && loss && n > 0, "fn_mse_mean_fwd: bad args");
+    mse_mean_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, y, n, loss);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+extern "C" int fn_mse_mean_bwd(const float* x, const float* y, long long n, const float* dloss, float* dx, void* stream) {
+    FN_REQUIRE(x && y && dloss && dx && n > 0, "fn_mse_mean_bwd: bad args");
+    mse_mean_bwd_kernel<<<fn_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, dloss, dx);
     FN_LAUNCH_CHECK();
     return FN_OK;
 }

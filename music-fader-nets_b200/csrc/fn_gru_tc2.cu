@@ -807,7 +807,8 @@ int launch2(K kernel, const Tc2Launch& P, int pairs, size_t smem, cudaStream_t s
     attrs[1].id = cudaLaunchAttributeCooperative;           // every CTA must be co-resident: they wait on each other
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 2;
+    static const int coop = env_int("FN_GRU2_COOP", 1);     // 0: no cooperative attribute (profilers that cannot replay cooperative cluster launches)
+    cfg.numAttrs = coop ? 2 : 1;
     int max_clusters = 0;
     FN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
     if (fits) { *fits = max_clusters * P.mc >= pairs; if (!*fits) return FN_OK; }

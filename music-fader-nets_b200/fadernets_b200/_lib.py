@@ -47,6 +47,7 @@ V, I, LL, F, SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 _SIGNATURES = {
     "fn_last_error": (C.c_char_p, []),
     "fn_abi_version": (I, []),
+    "fn_source_hash": (C.c_char_p, []),
     "fn_device_info": (I, [C.POINTER(I)] * 4),
     "fn_gemm_f32": (I, [V, LL, LL, V, LL, LL, V, LL, V, I, I, I, I, V]),
     "fn_tc_gemm_bf16": (I, [V, LL, I, V, LL, I, V, LL, I, V, I, I, I, I, V]),
@@ -69,6 +70,11 @@ _SIGNATURES = {
     "fn_ids_to_onehot": (I, [V, I, I, I, V, V]),
     "fn_ids_to_time_major": (I, [V, I, I, I, I, V, V]),
     "fn_transpose_f32": (I, [V, LL, V, LL, I, I, I, V]),
+    "fn_relu_mask_fwd": (I, [V, V, V, LL, V]),
+    "fn_relu_mask_bwd": (I, [V, V, V, V, LL, V]),
+    "fn_scale_f32": (I, [V, V, F, LL, V]),
+    "fn_mse_mean_fwd": (I, [V, V, LL, V, V]),
+    "fn_mse_mean_bwd": (I, [V, V, LL, V, V, V]),
     "fn_check_index_i64": (I, [V, LL, LL, V, V]),
     "fn_clamp_index_i32": (I, [V, LL, I, V, V]),
     "fn_clean_tokens": (I, [V, I, I, V, V, V]),
@@ -102,7 +108,7 @@ _SIGNATURES = {
     "fn_grad_norm": (I, [V, LL, V, V, SZ, V]),
     "fn_clip_adam": (I, [V, V, V, V, LL, V, F, F, F, F, F, I, V]),
 }
-_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_latent_scratch_bytes", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
+_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_source_hash", "fn_latent_scratch_bytes", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
               "fn_col_sum_scratch_bytes", "fn_reduce_scratch_bytes"}
 
 
@@ -126,6 +132,20 @@ class _Lib:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(dll, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
+        # the binary must have been built from the sources it ships with (no stale .so on the GPU box)
+        built = dll.fn_source_hash().decode()
+        try:
+            import importlib.util
+            root = os.path.dirname(os.path.dirname(_HERE))
+            spec = importlib.util.spec_from_file_location("_fn_graft_entry", os.path.join(root, "__graft_entry__.py"))
+            ge = importlib.util.module_from_spec(spec); spec.loader.exec_module(ge)
+            want = ge.source_hash()
+        except Exception:                       # package used outside the repo tree: nothing to compare with
+            want = None
+        if want is not None and built != want:
+            raise FaderNetsError(f"{LIB_PATH} was built from other sources (library {built}, tree {want}): "
+                                 "run `python __graft_entry__.py build`")
+        self.source_hash = built
         self._dll = dll
         return self
 

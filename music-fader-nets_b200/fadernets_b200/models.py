@@ -19,7 +19,7 @@ from torch.distributions import Normal
 from . import ops
 from ._lib import FaderNetsError, require_cuda
 from .ops import ChainSpec, GruGroupFn, LatentHeadFn, QyXFn, TimeLogSoftmaxFn, VocabLogSoftmaxFn, linear
-from .ops_bf16 import DecoderStackBf16Fn, GruGroupBf16Fn, linear_bf16
+from .ops_bf16 import DecoderStackBf16Fn, GruGroupBf16Fn, linear_bf16, GruGroupBf16
 
 PRECISIONS = ("f32", "bf16")
 
@@ -123,7 +123,7 @@ class _FaderBase(nn.Module):
         return self
 
     def _gru(self):
-        return GruGroupBf16Fn if self.precision == "bf16" else GruGroupFn
+        return GruGroupBf16 if self.precision == "bf16" else GruGroupFn
 
     def _tlinear(self, x, lin):
         """Linear over a T*B-row activation (time-major hidden states)."""

@@ -267,6 +267,9 @@ class GruGroupFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         specs, (B, T, H), keep = ctx.specs, ctx.dims, ctx.keep
+        if keep is None:
+            raise RuntimeError("fadernets_b200: backward through a GRU group a second time -- its saved states were freed "
+                               "by the first backward (retain_graph is not supported by this Function)")
         dev = keep[0]["hs"].device
         K3 = 3 * H
         gfinals = [None if g is None else _f32c(g) for g in grads[:ctx.n_finals]]
@@ -631,3 +634,62 @@ class LatentRegFn(torch.autograd.Function):
         dz = torch.empty((B, Z), dtype=F32, device=dz0.device)
         LIB.call("fn_latent_reg_bwd", _p(dz0), _p(dloss), B, Z, _p(dz), _st(dz))
         return dz, None
+
+
+# ------------------------------------------------------------------------------------------------
+# small pieces of the sibling models (MusicAttrFaderNets discriminator heads, adversarial MSE)
+# ------------------------------------------------------------------------------------------------
+class ReluMaskFn(torch.autograd.Function):
+    """y = relu(x) * mask -- `dropout(relu(x))` with the keep mask (already divided by 1 - p) drawn by the caller."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        x = _f32c(x)
+        mask = None if mask is None else _f32c(mask)
+        y = torch.empty_like(x)
+        LIB.call("fn_relu_mask_fwd", _p(x), _p(mask), _p(y), x.numel(), _st(x))
+        ctx.save_for_backward(x, mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mask = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        LIB.call("fn_relu_mask_bwd", _p(x), _p(mask), _p(_f32c(dy)), _p(dx), x.numel(), _st(x))
+        return dx, None
+
+
+class GradReverseFn(torch.autograd.Function):
+    """ReverseLayerF (model_v2.py:426-435): identity forward, gradient times -alpha."""
+
+    @staticmethod
+    def forward(ctx, x, alpha=1.0):
+        ctx.alpha = float(alpha)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32c(dy)
+        dx = torch.empty_like(dy)
+        LIB.call("fn_scale_f32", _p(dy), _p(dx), -ctx.alpha, dy.numel(), _st(dy))
+        return dx, None
+
+
+class MseMeanFn(torch.autograd.Function):
+    """torch.nn.MSELoss(reduction='mean')(x, y) over a batch vector (trainer_fader.py:107-108); no gradient into y."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.shape = x.shape
+        x, y = _f32c(x).reshape(-1), _f32c(y).reshape(-1)
+        loss = torch.empty((), dtype=F32, device=x.device)
+        LIB.call("fn_mse_mean_fwd", _p(x), _p(y), x.numel(), _p(loss), _st(x))
+        ctx.save_for_backward(x, y)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, y = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        LIB.call("fn_mse_mean_bwd", _p(x), _p(y), x.numel(), _p(_f32c(dloss)), _p(dx), _st(x))
+        return dx.view(ctx.shape), None

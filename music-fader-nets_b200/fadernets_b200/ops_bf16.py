@@ -277,6 +277,9 @@ class GruGroupBf16Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         specs, (B, T, H), keep = ctx.specs, ctx.dims, ctx.keep
+        if keep is None:
+            raise RuntimeError("fadernets_b200: backward through a GRU group a second time -- its saved states were freed "
+                               "by the first backward (retain_graph is not supported by this Function)")
         dev = keep[0]["hsx"].device
         K3, H4, TB = 3 * H, 4 * H, T * B
         n = len(specs)
@@ -316,6 +319,36 @@ class GruGroupBf16Fn(torch.autograd.Function):
             out_grads += _finish_chain_grads(sp, keep[ci], bufs[ci]["dg"], bufs[ci]["dh0"], B, T, H)
         ctx.keep = None
         return (None, None, None, None, None) + tuple(out_grads)
+
+
+class GruGroupBf16:
+    """GruGroupBf16Fn for any batch size: the tensor-core gate block handles at most 256 rows (two 128-row MMA tiles)
+    per chain, so a larger per-GPU batch is cut into independent groups of <= 256 sequences (a recurrence never mixes
+    sequences), each run through GruGroupBf16Fn, and the per-sequence outputs are concatenated.  Weight gradients add up
+    through autograd.  (The reference's nn.GRU has no batch limit: trainer_gmm.py uses batch_size 128 by default.)"""
+    MAX_ROWS = 256
+
+    @staticmethod
+    def apply(specs, B, T, H, final_widths, *tensors):
+        import dataclasses
+        if B <= GruGroupBf16.MAX_ROWS:
+            return GruGroupBf16Fn.apply(specs, B, T, H, final_widths, *tensors)
+        outs = []
+        for lo in range(0, B, GruGroupBf16.MAX_ROWS):
+            hi = min(B, lo + GruGroupBf16.MAX_ROWS)
+            sub_specs, sub_tensors, pos = [], [], 0
+            for sp in specs:
+                sub_specs.append(dataclasses.replace(sp, ids=None if sp.ids is None else sp.ids[:, lo:hi].contiguous()))
+                sub_tensors += list(tensors[pos:pos + 4]); pos += 4
+                if sp.z_cols is not None:
+                    sub_tensors.append(tensors[pos][lo:hi]); pos += 1
+                if sp.x_cols is not None:
+                    sub_tensors.append(tensors[pos][:, lo:hi].contiguous()); pos += 1
+                if sp.h0 == "tensor":
+                    sub_tensors.append(tensors[pos][lo:hi]); pos += 1
+            outs.append(GruGroupBf16Fn.apply(sub_specs, hi - lo, T, H, final_widths, *sub_tensors))
+        nf = len(final_widths)
+        return tuple(torch.cat([o[i] for o in outs], 0 if i < nf else 1) for i in range(len(outs[0])))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -422,6 +455,9 @@ class DecoderStackBf16Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_r, g_n, g_2):
         keep, (B, T, H), S = ctx.keep, ctx.dims, ctx.S
+        if keep is None:
+            raise RuntimeError("fadernets_b200: backward through the decoder stack a second time -- its saved states were "
+                               "freed by the first backward (retain_graph is not supported by this Function)")
         dev = keep[0]["hsx"].device
         K3, H4 = 3 * H, 4 * H
         L = T // S

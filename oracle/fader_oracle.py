@@ -450,3 +450,111 @@ def draw_eps(B: int, Z: int, T: int, training: bool = True):
     if training:
         torch.rand(T)
     return eps_r, eps_n
+
+
+# --------------------------------------------------------------------------- #
+# sibling models on the same blocks: model_v2.py:174-586         #
+# --------------------------------------------------------------------------- #
+SIBLING_DEAD = ("c_r.", "c_n.")                      # registered by the reference, never used in forward (model_v2.py:305-306, 458-459)
+
+
+def sibling_is_live(name: str) -> bool:
+    return not name.startswith(SIBLING_DEAD)
+
+
+def _bi_encoder(w: Weights, gru: str, d_ids: Tensor, extra: Optional[Tensor] = None):
+    """One bidirectional GRU over the event one-hots (plus `extra` (B,E): columns appended to every step's input,
+    model_v2.py:338-341) -> [h_fwd(T-1) | h_bwd(0)] -> mu = Linear, scale = exp(Linear) (model_v2.py:229-233, 343-347, 497-502)."""
+    B, T = d_ids.shape
+    V = EVENT_DIMS
+    hs = []
+    for sfx, rev in (("", False), ("_reverse", True)):
+        w_ih, w_hh = w[f"{gru}.weight_ih_l0{sfx}"], w[f"{gru}.weight_hh_l0{sfx}"]
+        b_ih, b_hh = w[f"{gru}.bias_ih_l0{sfx}"], w[f"{gru}.bias_hh_l0{sfx}"]
+        gi = w_ih[:, :V].t()[d_ids] + b_ih
+        if extra is not None:
+            gi = gi + (extra @ w_ih[:, V:].t())[:, None, :]
+        o = gru_seq(gi, torch.zeros(B, w_hh.shape[1], dtype=w_hh.dtype), w_hh, b_hh, reverse=rev)
+        hs.append(o[:, 0] if rev else o[:, T - 1])
+    hcat = torch.cat(hs, 1)
+    return hcat @ w["mu.weight"].t() + w["mu.bias"], torch.exp(hcat @ w["var.weight"].t() + w["var.bias"])
+
+
+def forward_sibling(w: Weights, kind: str, d_ids: Tensor, c: Tensor, r_density: Tensor, n_density: Tensor, eps: Tensor,
+                    mask_r: Optional[Tensor] = None, mask_n: Optional[Tensor] = None, training: bool = True):
+    """forward() of MusicAttrSingleVAE (model_v2.py:263-285), MusicAttrCVAE (:400-423) and MusicAttrFaderNets (:560-586)
+    with the noise (and, FaderNets, the two dropout masks incl. their 1/(1-p) scale) passed in explicitly.
+    r_density / n_density: (B,1) as the trainers pass them (trainer_cvae.py:122-125)."""
+    T = d_ids.shape[1]
+    res = {}
+    if kind == "singlevae":
+        mu, s = _bi_encoder(w, "gru", d_ids)
+        z = mu + s * eps
+        zc = torch.cat([z, c], 1)
+    elif kind == "cvae":
+        mu, s = _bi_encoder(w, "gru_e", d_ids, torch.cat([r_density, n_density], 1))
+        z = mu + s * eps
+        zc = torch.cat([z, r_density, n_density], 1)
+    else:
+        mu, s = _bi_encoder(w, "gru_e", d_ids)
+        z = mu + s * eps
+        # gradient reversal is the identity in forward (ReverseLayerF, :426-435); dropout(relu(linear)) (:574-575)
+        rz = GradReverse.apply(z)
+        r_out = torch.relu(rz @ w["discriminator_r.weight"].t() + w["discriminator_r.bias"])
+        n_out = torch.relu(rz @ w["discriminator_n.weight"].t() + w["discriminator_n.bias"])
+        res["r_out"] = r_out * mask_r if mask_r is not None else r_out
+        res["n_out"] = n_out * mask_n if mask_n is not None else n_out
+        zc = torch.cat([z, r_density, n_density], 1)
+    res.update(mu=mu, scale=s, z=zc, z_lat=z)
+    res["out"], res["fed"] = global_decoder(w, zc, T, d_ids if training else None)
+    return res
+
+
+class GradReverse(torch.autograd.Function):
+    """ReverseLayerF (model_v2.py:426-435): identity forward, negated gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.neg()
+
+
+def loss_sibling(kind: str, res, d, r_density, n_density, step: int, beta: float):
+    """trainer_singlevae.py:86-123, trainer_cvae.py:84-102, trainer_fader.py:84-110.  Returns (loss, named terms).
+    Quirks kept: the single-VAE trainer weights the KL with `beta` (not the annealed beta0) and the CE with 5."""
+    beta0 = beta_anneal(step, beta)
+    ce_x = nll_mean(res["out"], d)
+    kld = kl_normal(res["mu"], res["scale"], torch.zeros_like(res["mu"]), torch.ones_like(res["scale"])).mean()
+    if kind == "singlevae":
+        outs = []
+        for col, dens in ((0, r_density), (1, n_density)):
+            dens = np.asarray(dens, dtype=np.float64).reshape(-1)
+            sgn = torch.sign(torch.from_numpy(np.subtract.outer(dens, dens)).float()).to(res["z"].dtype)
+            dz = res["z"][:, col].reshape(-1, 1) - res["z"][:, col]
+            outs.append(((torch.tanh(dz) - sgn) ** 2).mean())
+        loss = 5 * ce_x + beta * kld + outs[0] + outs[1]
+        return loss, dict(CE_X=ce_x, l_r=outs[0], l_n=outs[1])
+    if kind == "cvae":
+        return ce_x + beta0 * kld, dict(CE_X=ce_x)
+    lmbda = min(step / 2000 * 1e-4, 1e-4)
+    l_r = lmbda * ((res["r_out"].squeeze() - r_density.squeeze()) ** 2).mean()
+    l_n = lmbda * ((res["n_out"].squeeze() - n_density.squeeze()) ** 2).mean()
+    return ce_x + beta0 * kld + l_r + l_n, dict(CE_X=ce_x, l_adv_r=l_r, l_adv_n=l_n)
+
+
+def sibling_loss_and_grads(w: Weights, kind: str, d, c, r_density, n_density, eps, step, beta, mask_r=None, mask_n=None):
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in w.items() if sibling_is_live(k)}
+    ww = {**w, **leaves}
+    rd = torch.as_tensor(np.asarray(r_density), dtype=torch.float32).reshape(-1, 1)
+    nd = torch.as_tensor(np.asarray(n_density), dtype=torch.float32).reshape(-1, 1)
+    res = forward_sibling(ww, kind, d, c, rd, nd, eps, mask_r, mask_n)
+    loss, terms = loss_sibling(kind, res, d, rd if kind != "singlevae" else r_density, nd if kind != "singlevae" else n_density,
+                               step, beta)
+    names = list(leaves)
+    gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, gs)}
+    scal = dict(loss=loss.detach(), **{k: v.detach() for k, v in terms.items()})
+    return scal, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in res.items()}

@@ -175,8 +175,124 @@ def make_case(variant: str, H: int, Z: int, K: int, B: int, T: int, seed: int):
     return g
 
 
+SIBLINGS = {"singlevae": ("MusicAttrSingleVAE", "trainer_singlevae.py"), "cvae": ("MusicAttrCVAE", "trainer_cvae.py"),
+            "fader": ("MusicAttrFaderNets", "trainer_fader.py")}
+
+
+def draw_sibling(kind, B, Zw, T):
+    """Consume the CPU default generator exactly as one training-mode forward of a sibling model does: the repar draw
+    (model_v2.py:273-276, 410-413, 569-572), FaderNets: the two dropout masks (:574-575), then T coin flips."""
+    eps = torch.normal(torch.zeros(B, Zw), torch.ones(B, Zw))
+    mr = mn = None
+    if kind == "fader":
+        mr = torch.nn.functional.dropout(torch.ones(B, 1), 0.3, True)
+        mn = torch.nn.functional.dropout(torch.ones(B, 1), 0.3, True)
+    torch.rand(T)
+    return eps, mr, mn
+
+
+def make_sibling_case(kind: str, H: int, Z: int, B: int, T: int, seed: int):
+    """Golden vectors of the sibling models (model_v2.py:174-586) driven through their own trainers' step functions
+    (trainer_singlevae.py:86-156, trainer_cvae.py:84-119, trainer_fader.py:84-139)."""
+    from oracle import fader_oracle as fo
+    gmm_model, model_v2 = load_reference()
+    cls, trainer = SIBLINGS[kind]
+    torch.manual_seed(seed)
+    model = getattr(model_v2, cls)(342, 3, 16, 24, H, Z, 32)
+    model.train()
+    args = dict(lr=1e-3, beta=0.2)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args["lr"])
+    ns = trainer_namespace(model, optimizer, args)
+    ns["Counter"] = __import__("collections").Counter
+    funcs = STEP_FUNCS + ("adversarial_loss",)
+    src = open(os.path.join(REF, trainer)).read()
+    tree = ast.parse(src)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in funcs]
+    exec(compile(ast.Module(body=body, type_ignores=[]), trainer, "exec"), ns)
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    d, r, n, c, r_density, n_density = fo.synth_batch(B, T, seed=seed + 1, pad_tail=True)
+    d_oh, r_oh, n_oh = (ns["convert_to_one_hot"](x, dims) for x, dims in ((d, 342), (r, 3), (n, 16)))
+    rd_t = torch.from_numpy(r_density).float().unsqueeze(-1)          # (B,1): trainer_cvae.py:122-125 / trainer_fader.py
+    nd_t = torch.from_numpy(n_density).float().unsqueeze(-1)
+    g = {"B": B, "T": T, "H": H, "Z": Z, "d": d.numpy(), "r": r.numpy(), "n": n.numpy(), "c": c.numpy(),
+         "r_density": r_density, "n_density": n_density}
+    for k, v in sd0.items():
+        g["w/" + k] = v.numpy()
+    STEP = 20000
+    Zw = 2 * Z if kind == "singlevae" else Z
+
+    def fwd():
+        if kind == "singlevae":
+            return model(d_oh, c)
+        return model(d_oh, r_oh, n_oh, c, rd_t, nd_t)
+
+    # ---- (1) forward + loss + gradients, noise replayed
+    torch.manual_seed(seed + 3)
+    eps, mr, mn = draw_sibling(kind, B, Zw, T)
+    g["eps"] = eps.numpy()
+    if mr is not None:
+        g["mask_r"], g["mask_n"] = mr.numpy(), mn.numpy()
+    torch.manual_seed(seed + 3)
+    res = fwd()
+    if kind == "fader":
+        (out, r_out, n_out), dis, z = res
+        g["r_out"], g["n_out"] = r_out.detach().numpy(), n_out.detach().numpy()
+    else:
+        out, dis, z = res
+    loss, CE_X = ns["loss_function"](out, d, dis, STEP, beta=0.2)
+    terms = {"CE_X": CE_X}
+    if kind == "singlevae":
+        l_r, l_n = ns["latent_regularized_loss_function"](z, r_density, n_density)
+        loss = loss + l_r + l_n
+        terms.update(l_r=l_r, l_n=l_n)
+    elif kind == "fader":
+        la_r, la_n = ns["adversarial_loss"](STEP, r_out, n_out, rd_t, nd_t)
+        loss = loss + la_r + la_n
+        terms.update(l_adv_r=la_r, l_adv_n=la_n)
+    optimizer.zero_grad()
+    loss.backward()
+    g["loss/loss"] = np.float64(loss.item())
+    for k, v in terms.items():
+        g["loss/" + k] = np.float64(v.item())
+    g["out"], g["mu"], g["scale"], g["z"] = out.detach().numpy(), dis.mean.detach().numpy(), dis.stddev.detach().numpy(), z.detach().numpy()
+    for k, p_ in model.named_parameters():
+        if p_.grad is not None:
+            g["grad/" + k] = p_.grad.detach().clone().numpy()
+
+    # ---- (2) two full train() calls from the initial weights
+    model.load_state_dict(sd0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args["lr"])
+    ns["optimizer"] = optimizer
+    torch.manual_seed(seed + 4)
+    traj, step = [], STEP
+    for it in range(2):
+        if kind == "singlevae":
+            step, o = ns["train"](step, d_oh, r_oh, n_oh, d, r, n, c, r_density, n_density)
+        else:
+            step, o = ns["train"](step, d_oh, r_oh, n_oh, d, r, n, c, rd_t, nd_t)
+        traj.append(o)
+    g["train/outputs"] = np.array(traj, dtype=np.float64)
+    for k, p_ in model.named_parameters():
+        if ("grad/" + k) in g:
+            g["w2/" + k] = p_.detach().clone().numpy()
+
+    # ---- (3) eval-mode greedy decode from the latent of (1)
+    model.load_state_dict(sd0)
+    model.eval()
+    with torch.no_grad():
+        dec = model.global_decoder(torch.from_numpy(g["z"]), steps=T + 4)
+    g["decode/tokens"] = dec.argmax(-1).numpy()
+    g["decode/logp"] = dec.numpy()
+    return g
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    for kind, H, Z, B, T, seed in (("singlevae", 16, 8, 3, 10, 40), ("cvae", 16, 8, 3, 10, 50), ("fader", 16, 8, 4, 9, 60)):
+        g = make_sibling_case(kind, H, Z, B, T, seed)
+        path = os.path.join(OUT, f"sib_{kind}_H{H}_Z{Z}_B{B}_T{T}.npz")
+        np.savez_compressed(path, **g)
+        print(path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: float(v) for k, v in g.items() if k.startswith("loss/")})
     for variant, H, Z, K, B, T, seed in (("gmvae", 16, 8, 2, 3, 12, 10), ("vae", 16, 8, 0, 4, 10, 20),
                                           ("gmvae", 32, 16, 3, 2, 9, 30)):
         g = make_case(variant, H, Z, K, B, T, seed)

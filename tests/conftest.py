@@ -12,7 +12,8 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN_FILES = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("sib_"))
+SIBLING_GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "sib_*.npz")))     # sibling models (oracle/gen_golden.py make_sibling_case)
 GOLDEN_SEEDS = {"gmvae_H16_Z8_B3_T12": 10, "vae_H16_Z8_B4_T10": 20, "gmvae_H32_Z16_B2_T9": 30}   # oracle/gen_golden.py main()
 
 

@@ -73,3 +73,69 @@ def test_training_phase_and_checkpoint_round_trip(lib, tmp_path):
     assert step_a == step_b and ha[0]["yamaha"]["train"] == hb[0]["yamaha"]["train"]
     for k, t in model2.state_dict().items():
         assert torch.equal(t, w_a[k]), k
+
+
+@pytest.mark.gpu
+def test_training_phase_against_oracle(lib):
+    """The epoch loop (reference trainer_gmm.py:306-467: supervised VGMIDI pass, then the unsupervised Yamaha pass,
+    evaluate() with step - 1) against the CPU oracle driven batch by batch with the same CPU-generator draws: the
+    per-epoch means of the 8 terms and the final weights."""
+    import fadernets_b200 as fn
+    from fadernets_b200 import data as D, trainer_gmm as T
+    from oracle import fader_oracle as fo
+    dev = torch.device("cuda:0")
+    H, Z, K = 16, 8, 2
+    w = fo.init_weights(H, Z, "gmvae", K, seed=1)
+    model = fn.MusicAttrRegGMVAE(342, 3, 16, 24, H, Z, 32, n_component=K)
+    model.load_state_dict(w)
+    model = model.to(dev).train()
+    opt = fn.FusedAdam(model, lr=1e-3)
+    y = D.synthetic_yamaha(20, 10, seed=0)
+    v = D.synthetic_vgmidi(20, 10, seed=1)
+    loaders = {"train": DataLoader(D.YamahaDataset(*y, mode="train"), batch_size=8),
+               "val": DataLoader(D.YamahaDataset(*y, mode="val"), batch_size=8),
+               "vgm_train": DataLoader(D.VGMIDIDataset(v[0], v[1], v[2], v[5], v[3], v[4], mode="train"), batch_size=6),
+               "vgm_val": DataLoader(D.VGMIDIDataset(v[0], v[1], v[2], v[5], v[3], v[4], mode="val"), batch_size=6)}
+    T.configure(model, opt, {"beta": 0.2, "lr": 1e-3, "n_epochs": 1})
+    step0 = 20000
+    torch.manual_seed(9)
+    step, hist = T.training_phase(step0, loaders, log=None)
+
+    # ---- oracle: same order of batches, same draws (every forward consumes eps_r, eps_n and T coin flips)
+    torch.manual_seed(9)
+    wo = {k: t.clone() for k, t in w.items()}
+    st = fo.AdamState(wo)
+    names = ("loss", "CE_X", "CE_R", "CE_N", "l_r", "l_n", "kld_latent", "kld_class")
+    ostep = step0
+    expect = {}
+    for tag, sup in (("vgm", True), ("", False)):
+        for split, training in (("train", True), ("val", False)):
+            tot, nb = np.zeros(8), 0
+            for x in loaders[f"{tag}_{split}" if tag else split]:
+                if sup:
+                    d, r, n, c, a, val, rd, nd = x
+                else:
+                    d, r, n, c, rd, nd = x
+                    a = None
+                d, r, n, c = d.long(), r.long(), n.long(), c.float()
+                er, en = fo.draw_eps(d.shape[0], Z, d.shape[1])
+                batch = (d, r, n, c, rd.numpy(), nd.numpy())
+                ylab = None if a is None else a.long()
+                if training:
+                    s, _ = fo.train_step(wo, st, "gmvae", batch, er, en, ostep, 0.2, 1e-3, y_label=ylab)
+                    ostep += 1
+                else:
+                    s, _, _ = fo.loss_and_grads(wo, "gmvae", batch, er, en, ostep - 1, 0.2, y_label=ylab)
+                row = [float(s["loss"]),
+                       float(s["CE_X"]), float(s["CE_R"]), float(s["CE_N"]), float(s["l_r"]), float(s["l_n"]),
+                       float(s["kld_lat_r"]) + float(s["kld_lat_n"]), float(s["kld_cls_r"]) + float(s["kld_cls_n"])]
+                tot += np.array(row); nb += 1
+            expect[("vgmidi" if sup else "yamaha", split)] = dict(zip(names, tot / nb))
+    assert step == ostep
+    for (part, split), ref in expect.items():
+        got = hist[0][part][split]
+        for k in names[1:]:
+            assert abs(got[k] - ref[k]) <= 1e-3 * max(1.0, abs(ref[k])), (part, split, k, got[k], ref[k])
+    sd = model.state_dict()
+    for k in ("grucell_g.weight_hh", "gru_r.weight_ih_l0", "mu_n_lookup.weight", "linear_out_g.bias"):
+        assert torch.allclose(sd[k].cpu(), wo[k], rtol=1e-3, atol=3e-5), k

@@ -64,3 +64,55 @@ def test_shift_and_arousal_transfer_batched(lib):
     torch.manual_seed(3)
     eps = torch.distributions.Normal(0, 1).sample(sample_shape=z.size()).to(dev)
     assert torch.equal(a, z + z.abs() * eps)
+
+
+def test_shift_against_oracle(lib):
+    """RhythmEvaluator.shift / NoteEvaluator.shift (test_class.py:233-254, 282-303): forward -> re-draw z from the
+    returned distributions -> overwrite latent dim 0 -> eval-mode greedy decode, against the CPU oracle replaying the same
+    CPU-generator draws (forward: eps_r, eps_n, T coin flips; then the two repar draws): tokens bit-exact, log-probs 1e-3."""
+    import fadernets_b200 as fn
+    from fadernets_b200 import evaluate as E
+    dev = torch.device("cuda:0")
+    H, Z, K, B, T, steps = 32, 16, 2, 5, 10, 14
+    w = fo.init_weights(H, Z, "gmvae", K, seed=2)
+    d, r, n, c, rd, nd = fo.synth_batch(B, T, seed=3)
+    for attr, target in (("rhythm", 0.7), ("note", -1.3)):
+        m = fn.MusicAttrRegGMVAE(342, 3, 16, 24, H, Z, 32, n_component=K)
+        m.load_state_dict(w)
+        m = m.to(dev).train()
+        torch.manual_seed(11)
+        out, z0 = E.shift(m, d.to(dev), r.to(dev), n.to(dev), c, target_z_value=target, attr=attr, steps=steps)
+        # ---- oracle with the same draws
+        torch.manual_seed(11)
+        er, en = fo.draw_eps(B, Z, T)
+        res = fo.forward(w, "gmvae", d, r, n, c, er, en)
+        e2r = torch.distributions.Normal(0, 1).sample(sample_shape=res["scale_r"].size())
+        e2n = torch.distributions.Normal(0, 1).sample(sample_shape=res["scale_n"].size())
+        z_r, z_n = res["mu_r"] + res["scale_r"] * e2r, res["mu_n"] + res["scale_n"] * e2n
+        z_sel = z_r if attr == "rhythm" else z_n
+        z0_ref = z_sel[:, 0].clone()
+        z_sel[:, 0] = target
+        lp_ref, tok_ref = fo.global_decoder(w, torch.cat([z_r, z_n, c], 1), steps)
+        assert torch.allclose(z0.cpu(), z0_ref, rtol=1e-4, atol=1e-5)
+        assert torch.equal(out.argmax(-1).cpu(), tok_ref), attr
+        assert float((out.cpu() - lp_ref).abs().max()) < 1e-3 * max(1.0, float(lp_ref.abs().max()))
+
+
+def test_arousal_transfer_against_oracle(lib):
+    """arousal_transfer.ipynb cells 11/15/17: shift vectors mu_lookup(1) - mu_lookup(0), encode, z = mean + lam * shift,
+    greedy decode: tokens bit-exact against the CPU oracle (fp32 path)."""
+    import fadernets_b200 as fn
+    from fadernets_b200 import evaluate as E
+    dev = torch.device("cuda:0")
+    H, Z, K, B, T, steps = 32, 16, 2, 6, 12, 20
+    w = fo.init_weights(H, Z, "gmvae", K, seed=4)
+    m = fn.MusicAttrRegGMVAE(342, 3, 16, 24, H, Z, 32, n_component=K)
+    m.load_state_dict(w)
+    m = m.to(dev)
+    d, r, n, c, rd, nd = fo.synth_batch(B, T, seed=5)
+    toks = E.arousal_transfer(m, d.to(dev), c, lam=0.5, steps=steps, sample=False)
+    mu_r, s_r, mu_n, s_n = fo.encode(w, d)
+    sr = w["mu_r_lookup.weight"][1] - w["mu_r_lookup.weight"][0]
+    sn = w["mu_n_lookup.weight"][1] - w["mu_n_lookup.weight"][0]
+    _, tok_ref = fo.global_decoder(w, torch.cat([mu_r + 0.5 * sr, mu_n + 0.5 * sn, c], 1), steps)
+    assert torch.equal(toks.cpu(), tok_ref)

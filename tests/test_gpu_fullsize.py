@@ -99,8 +99,20 @@ def test_tensor_core_path_limits_fail_loudly(dev):
     with pytest.raises(FaderNetsError, match="64"):            # H % 64 != 0: no silent fallback to another path
         m(b[0], b[1], b[2], b[3])
     m = fn.MusicAttrRegGMVAE(342, 3, 16, 24, 64, 16, 32, n_component=2).to(dev).train().set_precision("bf16")
+    # a batch above the 256 rows one chain holds is cut into groups of <= 256 sequences (ops_bf16.GruGroupBf16):
+    # same results as the fp32 path within bf16 tolerance, gradients flow to every parameter
     b = _batch(300, 8, 0, dev)
-    with pytest.raises(FaderNetsError, match="256"):           # one chain holds at most 256 rows
-        m(b[0], b[1], b[2], b[3])
+    torch.manual_seed(5)
+    res16 = m(b[0], b[1], b[2], b[3])
+    out16 = res16[0][0]
+    assert out16.shape[0] == 300 and torch.isfinite(out16).all()
+    out16.float().sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for _, p in m.live_parameters())
+    assert float(dict(m.named_parameters())["gru_r.weight_hh_l0"].grad.abs().sum()) > 0
+    m.set_precision("f32")
+    torch.manual_seed(5)
+    out32 = m(b[0], b[1], b[2], b[3])[0][0]
+    assert float((out16 - out32).abs().max()) < 5e-2
+    m.set_precision("bf16")
     with pytest.raises(FaderNetsError):
         m.set_precision("fp8")

@@ -1,0 +1,105 @@
+"""Sibling models on the same CUDA blocks (model_v2.py:174-586 with trainer_singlevae.py /
+trainer_cvae.py / trainer_fader.py) against golden vectors of the UNMODIFIED reference: state_dict keys, forward outputs,
+loss terms, every gradient, two train() calls incl. updated weights, greedy tokens bit-exact (fp32 path, 1e-3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import SIBLING_GOLDEN_FILES
+from test_oracle_siblings import load
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-3
+
+
+def _make(kind, g, dev):
+    import fadernets_b200 as fn
+    cls = {"singlevae": fn.MusicAttrSingleVAE, "cvae": fn.MusicAttrCVAE, "fader": fn.MusicAttrFaderNets}[kind]
+    m = cls(342, 3, 16, 24, int(g["H"]), int(g["Z"]), 32)
+    assert list(m.state_dict().keys()) == list(g["weights"].keys())          # the reference's keys, in its order
+    m.load_state_dict(g["weights"])
+    return m.to(dev).train()
+
+
+def _trainer(kind):
+    from fadernets_b200 import trainer_siblings as TS
+    return {"singlevae": TS.SingleVAETrainer, "cvae": TS.CVAETrainer, "fader": TS.FaderTrainer}[kind]()
+
+
+def close(a, b, what, rtol=RTOL, atol=2e-5):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double()
+    err = float((a - b).abs().max())
+    assert err <= atol + rtol * float(b.abs().max()), (what, err)
+
+
+@pytest.mark.parametrize("path", SIBLING_GOLDEN_FILES, ids=[os.path.basename(p)[:-4] for p in SIBLING_GOLDEN_FILES])
+def test_sibling_models_match_reference(lib, path):
+    import fadernets_b200 as fn
+    g = load(path)
+    kind = g["kind"]
+    dev = torch.device("cuda:0")
+    seed = {"singlevae": 40, "cvae": 50, "fader": 60}[kind]
+    m = _make(kind, g, dev)
+    tr = _trainer(kind)
+    opt = fn.FusedAdam(m, lr=1e-3)
+    tr.configure(m, opt, {"beta": 0.2, "lr": 1e-3})
+    d, r, n, c = (torch.from_numpy(g[k]).to(dev) for k in ("d", "r", "n", "c"))
+    d_oh, r_oh, n_oh = tr.convert_to_one_hot(d, 342), tr.convert_to_one_hot(r, 3), tr.convert_to_one_hot(n, 16)
+    rd, nd = g["r_density"], g["n_density"]
+    rd_t = torch.from_numpy(rd).float().unsqueeze(-1)
+    nd_t = torch.from_numpy(nd).float().unsqueeze(-1)
+    dens = (rd, nd) if kind == "singlevae" else (rd_t, nd_t)
+
+    # ---- forward + losses + gradients with the reference's draws (CPU generator, same seed)
+    opt.zero_grad()
+    torch.manual_seed(seed + 3)
+    if kind == "singlevae":
+        terms = tr._losses(20000, d_oh, d, c, *dens)
+    else:
+        terms = tr._losses(20000, d_oh, r_oh, n_oh, d, c, *dens)
+    names = {"singlevae": ("loss", "CE_X", "l_r", "l_n"), "cvae": ("loss", "CE_X"), "fader": ("loss", "CE_X", "l_adv_r", "l_adv_n")}[kind]
+    for nm, t in zip(names, terms):
+        e = float(g["loss/" + nm])
+        assert abs(float(t) - e) <= RTOL * max(1.0, abs(e)) + 1e-9, (nm, float(t), e)
+    terms[0].backward()
+    params = dict(m.named_parameters())
+    ng = 0
+    for k, v in g.items():
+        if k.startswith("grad/"):
+            close(params[k[5:]].grad, v, k, atol=1e-6)
+            ng += 1
+    assert ng >= 20
+    # forward outputs
+    torch.manual_seed(seed + 3)
+    res = m(d_oh, c) if kind == "singlevae" else m(d_oh, r_oh, n_oh, c, rd_t, nd_t)
+    if kind == "fader":
+        (out, r_out, n_out), dis, z = res
+        close(r_out, g["r_out"], "r_out", atol=1e-6); close(n_out, g["n_out"], "n_out", atol=1e-6)
+    else:
+        out, dis, z = res
+    close(out, g["out"], "out"); close(dis.mean, g["mu"], "mu"); close(dis.stddev, g["scale"], "scale"); close(z, g["z"], "z")
+
+    # ---- two full train() calls from the initial weights
+    m.load_state_dict(g["weights"])
+    opt = fn.FusedAdam(m, lr=1e-3)
+    tr.configure(m, opt, {"beta": 0.2, "lr": 1e-3})
+    torch.manual_seed(seed + 4)
+    step = 20000
+    for it in range(2):
+        step, o = tr.train(step, d_oh, r_oh, n_oh, d, r, n, c, *dens)
+        for a, b in zip(o, g["train/outputs"][it]):
+            assert abs(a - b) <= RTOL * max(1.0, abs(b)) + 1e-9, (it, o, g["train/outputs"][it])
+    sd = m.state_dict()
+    for k, v in g.items():
+        if k.startswith("w2/"):
+            close(sd[k[3:]], v, k, rtol=1e-3, atol=3e-5)
+
+    # ---- eval-mode greedy decode: tokens bit-exact
+    m.load_state_dict(g["weights"])
+    m.eval()
+    zt = torch.from_numpy(g["z"]).to(dev)
+    lp = m.global_decoder(zt, g["decode/tokens"].shape[1])
+    assert np.array_equal(lp.argmax(-1).cpu().numpy(), g["decode/tokens"])
+    close(lp, g["decode/logp"], "decode log-probs", atol=1e-4)

@@ -33,8 +33,9 @@ if os.path.exists(src):
 
 # ---- full capture of the GRU kernels -------------------------------------------------------------------------------
 rep = os.path.join(G, f"{tag}_gru_tc_c3.ncu-rep")
-if os.path.exists(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = os.path.join(G, f"{tag}_gru_tc_c3_raw.csv")          # `ncu -i ... --page raw --csv` already run on the GPU box (the report itself is too big to bring back)
+if os.path.exists(rep) or os.path.exists(raw):
+    out = open(raw).read() if os.path.exists(raw) else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h, units = rows[0], rows[1]
     keep = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
@@ -44,7 +45,20 @@ if os.path.exists(rep):
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
     traffic = 0.0
     with open(os.path.join(P, f"{tag}_ncu_gru_tc_c3_bf16.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none, bench.py --workload c3 (B=256,T=512,H=1024,bf16): the {len(rows) - 2} gru_tc_kernel launches of ONE train step\n")
+        f.write(f"# ncu --set full --clock-control none, bench.py --workload c3 (B=256,T=512,H=1024,bf16): the {len(rows) - 2} GRU kernel launches of ONE train step\n")
+        f.write("# (FN_GRU2_COOP=0: ncu cannot replay cooperative cluster launches; same kernels, same cluster shape)\n")
+        tens = {}
+        for r in rows[2:]:
+            nm = r[h.index('Kernel Name')]
+            kk = "fwd" if "fwd" in nm else "bwd"
+            try:
+                dur = float(r[h.index("gpu__time_duration.sum")]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(units[h.index("gpu__time_duration.sum")], 1.0)
+                tp = float(r[h.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")])
+                a = tens.setdefault(kk, [0.0, 0.0]); a[0] += dur * tp; a[1] += dur
+            except Exception:
+                pass
+        for kk, (num, den) in tens.items():
+            f.write(f"# {kk}: duration-weighted sm__pipe_tensor_cycles_active (pct of peak, elapsed) = {num / max(den, 1e-9):.1f} % over {den / 1e3:.2f} ms of launches\n")
         for r in rows[2:]:
             f.write(f"--- {r[h.index('Kernel Name')][:110]}\n")
             for k in keep:
