@@ -46,6 +46,9 @@ WORKLOADS = {
     "c1": ("vae", 4, 128, 256, 128, 0, "f32"),
     "c2": ("gmvae", 64, 256, 512, 128, 2, "f32"),
     "c2_bf16": ("gmvae", 64, 256, 512, 128, 2, "bf16"),
+    # the fp32 parity bar on the tensor cores: hi / lo bf16 operand planes, three plane products per product (bf16x3 mode)
+    "c2_x3": ("gmvae", 64, 256, 512, 128, 2, "bf16x3"),
+    "c3_x3": ("gmvae", 256, 512, 1024, 128, 2, "bf16x3"),
     "c3": ("gmvae", 256, 512, 1024, 128, 2, "bf16"),
     "c3_f32": ("gmvae", 256, 512, 1024, 128, 2, "f32"),
     # BASELINE configs[4]: arousal-transfer inference (encode -> shift z -> greedy decode), seq_len 512
@@ -275,13 +278,15 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": ("gru2_fwd_kernel + gru2_bwd_kernel (persistent tcgen05 cta_group::2 recurrent GEMM + gates, CTA pairs)" if prec == "bf16" else
+                                "gru_tc_kernel<.., X3> (persistent tcgen05 recurrent GEMM over hi / lo bf16 planes: 3 tensor-core products per algorithmic product)" if prec == "bf16x3" else
                                 "gru_fwd_kernel + gru_bwd_kernel (persistent fp32 SIMT recurrent GEMM + gates)"),
                      "bound": "tensor", "achieved": round(achieved, 3) if achieved else None,
                      "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                      "frac": round(achieved / peaks["tf_sust"], 5) if achieved else None,
                      "traffic": ncu_traffic(args.workload),
                      "peak_source": peaks["src"] + " cuBLAS bf16 sustained (kernel timed inside a long step)" +
-                                    ("" if prec == "bf16" else "; fp32 SIMT exact-parity path (FMA pipe, no tensor cores)"),
+                                    ("" if prec == "bf16" else "; achieved counts ALGORITHMIC FLOP (the tensor cores execute 3x that)" if prec == "bf16x3"
+                                     else "; fp32 SIMT exact-parity path (FMA pipe, no tensor cores)"),
                      "flops_per_launch_group": gru_flops, "ms_per_step_in_kernel": round(gru_ms, 3) if gru_ms else None,
                      "step_flops": flops_per_token(H) * tokens,
                      "step_frac_of_peak": round(flops_per_token(H) * tokens * world / (sec / args.steps) / 1e12 / (peaks["tf_sust"] * world), 5)},
@@ -442,7 +447,7 @@ def cpu_decode_reference(T, H, Z, K, Bs=8):
             "sample": f"1 batch of {Bs} sequences x {T} steps, hidden {H}, fp32, unmodified reference classes in eval mode; {sec:.2f} s"}
 
 
-SAMPLE_BATCH = {"c1": 4, "c2": 8, "c2_bf16": 8, "c3": 4, "c3_f32": 4}     # the batch at which the CPU reference is fastest per sequence
+SAMPLE_BATCH = {"c1": 4, "c2": 8, "c2_bf16": 8, "c2_x3": 8, "c3": 4, "c3_f32": 4, "c3_x3": 4}     # the batch at which the CPU reference is fastest per sequence
 
 
 def workload_config(workload, world):

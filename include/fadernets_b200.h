@@ -169,6 +169,35 @@ int fn_gru_seq_bwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T
                         size_t barrier_ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * bf16x3 mode: the fp32 parity bar (1e-3 relative, BASELINE config 2) ON the tensor cores.  Every fp32 value that feeds a
+ * T-scale product is carried as TWO bf16 planes, hi = bf16(x) and lo = bf16(x - hi) (16 mantissa bits together), and every
+ * product is evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (the dropped lo*lo term is ~2^-16 relative).
+ * Same kernels, same call sites as the bf16 entry points above; what changes is the storage:
+ *   hsx    bf16 [T+1][B][2H]  columns [0,H) = hi, [H,2H) = lo;
+ *   gates  bf16, T * ceil32(B) * 8H elements (opaque: the 4H hi columns then the 4H lo columns of a row, 32x16 blocks);
+ *   dg     bf16 [T][B][8H]    columns [0,4H) = hi of (dr, dz, dn, dn*r), [4H,8H) = lo;
+ *   w_hh   bf16 [3H][3H]  = [hi | hi | lo] of W_hh along K (fn_split_bf16 with hi2_off);  w_hh_t bf16 [H][9H] likewise;
+ *   emb, dense, dhs are FP32 ([Vin][3H], [T][B][3H], [T][B][H]); sigma / tanh are evaluated with exp, not tanh.approx.
+ * B <= 256 rows per chain, H % 64 == 0.
+ * ---------------------------------------------------------------------------------------- */
+int fn_gru_seq_fwd_bf16x3(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                          size_t barrier_ws_bytes, void* stream);
+int fn_gru_seq_bwd_bf16x3(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                          size_t barrier_ws_bytes, void* stream);
+/* Tensor-core GEMM over hi / lo planes: C fp32|bf16 = (A_hi + A_lo)(B_hi + B_lo) - A_lo B_lo, one fp32 accumulator.
+ * a_lo_off / b_lo_off: element offset of the operand's lo plane from its hi plane (same leading dimension); 0 = the
+ * operand is exact in bf16 (e.g. a one-hot) and contributes one plane.  Other arguments as fn_tc_gemm_bf16_splitk. */
+int fn_tc_gemm_bf16x3(const void* A, long long lda, long long a_lo_off, int a_mn_major, const void* B, long long ldb,
+                      long long b_lo_off, int b_mn_major, void* C, long long ldc, int c_bf16, const float* bias, int M, int N,
+                      int K, int accumulate, int splits, void* workspace, size_t ws_bytes, void* stream);
+/* fp32 -> (hi, lo) bf16 planes with arbitrary source strides: dst[r*ld_dst + c] = hi, dst[r*ld_dst + lo_off + c] = lo and,
+ * if hi2_off >= 0, a second copy of hi at dst[r*ld_dst + hi2_off + c] (the [hi | hi | lo] weight layout above). */
+int fn_split_bf16(const float* src, long long s_r, long long s_c, void* dst, long long ld_dst, long long rows, long long cols,
+                  long long lo_off, long long hi2_off, void* stream);
+/* fn_time_sum_bf16 over the split stream dg [T][B][8H] (sums hi + lo). */
+int fn_time_sum_bf16x3(const void* dg, int B, int T, int H, float* dproj, float* dghsum, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Greedy decode of the global decoder as ONE persistent kernel (eval-mode global_decoder, gmm_model.py:119-149
  * with _sampling :73-80; drivers test_class.py:233-254, arousal_transfer.ipynb cells 15/17): per step cell 1
  * (token gather + z projection) -> cell 2 -> vocabulary projection -> first arg-max -> next token, all `steps` on

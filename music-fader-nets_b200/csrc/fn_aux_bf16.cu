@@ -42,6 +42,37 @@ __global__ void cast_bf16_vec_kernel(const float* __restrict__ src, __nv_bfloat1
     reinterpret_cast<uint4*>(dst)[i] = o;
 }
 
+// bf16x3 mode: an fp32 value is carried as TWO bf16 planes, hi = bf16(x) and lo = bf16(x - hi) (16 mantissa bits together);
+// dst[r*ld + c] = hi, dst[r*ld + lo_off + c] = lo, and (weights of the recurrent kernels, whose K loop runs over the three
+// plane products hi*hi, lo*hi, hi*lo) optionally a second copy of hi at hi2_off.  Same tiling as cast_bf16_kernel.
+__device__ __forceinline__ void split_store(__nv_bfloat16* d, long long lo_off, long long hi2_off, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    d[0] = hi;
+    d[lo_off] = __float2bfloat16(v - __bfloat162float(hi));
+    if (hi2_off >= 0) d[hi2_off] = hi;
+}
+__global__ void split_bf16_kernel(const float* __restrict__ src, long long s_r, long long s_c, __nv_bfloat16* __restrict__ dst,
+                                  long long ld_dst, long long rows, long long cols, long long lo_off, long long hi2_off) {
+    __shared__ float tile[32][33];
+    const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    if (s_c == 1) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const long long r = r0 + i, c = c0 + threadIdx.x;
+            if (r < rows && c < cols) split_store(dst + r * ld_dst + c, lo_off, hi2_off, src[r * s_r + c]);
+        }
+        return;
+    }
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long c = c0 + i, r = r0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * s_r + c * s_c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const long long r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) split_store(dst + r * ld_dst + c, lo_off, hi2_off, tile[threadIdx.x][i]);
+    }
+}
+
 __global__ void ids_to_onehot_bf16_kernel(const int32_t* __restrict__ ids, long long rows, int V, long long ld,
                                           __nv_bfloat16* __restrict__ oh) {
     // one warp per row, 8 bf16 (16 B) per lane per pass
@@ -62,26 +93,40 @@ __global__ void ids_to_onehot_bf16_kernel(const int32_t* __restrict__ ids, long 
 }
 
 // dg [T][B][4H] bf16, columns (dr, dz, dn, dn*r).  One thread per (b, column pair).
+// X3: rows of 8H = the hi planes followed by the lo planes (bf16x3 mode); the sum adds both.
+template <bool X3>
 __global__ void time_sum_bf16_kernel(const __nv_bfloat16* __restrict__ dg, int B, int T, int H, float* __restrict__ dproj,
                                      float* __restrict__ dghsum) {
-    const int H4 = 4 * H, K3 = 3 * H;
+    const int H4 = 4 * H, K3 = 3 * H, P = X3 ? 8 * H : 4 * H;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * (H4 / 2)) return;
     const int b = (int)(i / (H4 / 2)), c = (int)(i % (H4 / 2)) * 2;
-    const __nv_bfloat16* p = dg + (long long)b * H4 + c;
-    const long long stride = (long long)B * H4;
+    const __nv_bfloat16* p = dg + (long long)b * P + c;
+    const long long stride = (long long)B * P;
     float s0 = 0.f, s1 = 0.f;
     int t = 0;
     for (; t + 4 <= T; t += 4) {
-        uint32_t w[4];
+        uint32_t w[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = __ldg(reinterpret_cast<const uint32_t*>(p + (t + j) * stride));
+        for (int j = 0; j < 4; ++j) {
+            w[j] = __ldg(reinterpret_cast<const uint32_t*>(p + (t + j) * stride));
+            if (X3) l[j] = __ldg(reinterpret_cast<const uint32_t*>(p + (t + j) * stride + H4));
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s0 += __uint_as_float(w[j] << 16); s1 += __uint_as_float(w[j] & 0xffff0000u); }
+        for (int j = 0; j < 4; ++j) {
+            float a0 = __uint_as_float(w[j] << 16), a1 = __uint_as_float(w[j] & 0xffff0000u);
+            if (X3) { a0 += __uint_as_float(l[j] << 16); a1 += __uint_as_float(l[j] & 0xffff0000u); }
+            s0 += a0; s1 += a1;
+        }
     }
     for (; t < T; ++t) {
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + t * stride));
-        s0 += __uint_as_float(w << 16); s1 += __uint_as_float(w & 0xffff0000u);
+        float a0 = __uint_as_float(w << 16), a1 = __uint_as_float(w & 0xffff0000u);
+        if (X3) {
+            const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(p + t * stride + H4));
+            a0 += __uint_as_float(l << 16); a1 += __uint_as_float(l & 0xffff0000u);
+        }
+        s0 += a0; s1 += a1;
     }
     float* rowp = dproj ? dproj + (long long)b * K3 : nullptr;
     float* rowh = dghsum ? dghsum + (long long)b * K3 : nullptr;
@@ -156,8 +201,33 @@ extern "C" int fn_ids_to_onehot_bf16(const int32_t* ids, long long rows, int V, 
 extern "C" int fn_time_sum_bf16(const void* dg, int B, int T, int H, float* dproj, float* dghsum, void* stream) {
     FN_REQUIRE(dg && (dproj || dghsum) && B > 0 && T > 0 && H > 0 && H % 2 == 0, "fn_time_sum_bf16: bad args");
     const long long n = (long long)B * 2 * H;
-    time_sum_bf16_kernel<<<fn_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dg, B, T, H, dproj, dghsum);
+    time_sum_bf16_kernel<false><<<fn_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dg, B, T, H, dproj, dghsum);
     FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+
+extern "C" int fn_time_sum_bf16x3(const void* dg, int B, int T, int H, float* dproj, float* dghsum, void* stream) {
+    FN_REQUIRE(dg && (dproj || dghsum) && B > 0 && T > 0 && H > 0 && H % 2 == 0, "fn_time_sum_bf16x3: bad args");
+    const long long n = (long long)B * 2 * H;
+    time_sum_bf16_kernel<true><<<fn_cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dg, B, T, H, dproj, dghsum);
+    FN_LAUNCH_CHECK();
+    return FN_OK;
+}
+
+extern "C" int fn_split_bf16(const float* src, long long s_r, long long s_c, void* dst, long long ld_dst, long long rows,
+                             long long cols, long long lo_off, long long hi2_off, void* stream) {
+    FN_REQUIRE(src && dst && rows > 0 && cols > 0 && lo_off != 0, "fn_split_bf16: bad args");
+    dim3 block(32, 8);
+    // rows can be T*B (hundreds of thousands): launch in groups of 65535 row blocks
+    const long long row_blocks = fn_cdiv(rows, 32);
+    for (long long rb0 = 0; rb0 < row_blocks; rb0 += 65535) {
+        const long long nb = row_blocks - rb0 < 65535 ? row_blocks - rb0 : 65535;
+        dim3 g(fn_cdiv(cols, 32), (unsigned)nb);
+        const long long r0 = rb0 * 32;
+        split_bf16_kernel<<<g, block, 0, (cudaStream_t)stream>>>(src + r0 * s_r, s_r, s_c, (__nv_bfloat16*)dst + r0 * ld_dst, ld_dst,
+                                                                 rows - r0 < nb * 32 ? rows - r0 : nb * 32, cols, lo_off, hi2_off);
+        FN_LAUNCH_CHECK();
+    }
     return FN_OK;
 }
 

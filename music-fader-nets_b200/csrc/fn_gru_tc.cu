@@ -111,13 +111,38 @@ struct TcLaunch {
 // 32 consecutive rows x 16 (or 8) consecutive units, i.e. exactly one block per gate, so its loads and stores are
 // contiguous 512-1024 B instead of 32 sectors 8 KB apart (the epilogues are LSU-transaction bound).
 
-template <int U, int NBT, bool BWD>
+// ---- bf16x3 mode (X3): every fp32 value that feeds a tensor-core product is carried as two bf16 planes, hi = bf16(x) and
+// lo = bf16(x - hi) (16 mantissa bits), and the K loop runs over the three plane products hi*hi + lo*hi + hi*lo with fp32
+// accumulation -- fp32-level results (~2^-16 relative per product) at bf16 tensor-core rate / 3.  State slabs are
+// [B][2H] (hi | lo), saved gates [..][8H] (the 4H hi columns, then the 4H lo columns, same 32x16 blocks), the gate-gradient
+// stream [B][8H]; token embeddings, the dense input stream and dhs are fp32; sigma / tanh use exp (not tanh.approx).
+template <int W>
+__device__ __forceinline__ void ld_split(const __nv_bfloat16* p, long long lo_off, float (&v)[W]) {
+    uint32_t a[W / 2], b[W / 2];
+    ldb_raw<W>(p, a, false); ldb_raw<W>(p + lo_off, b, false);
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) { v[2 * i] = bf_lo(a[i]) + bf_lo(b[i]); v[2 * i + 1] = bf_hi(a[i]) + bf_hi(b[i]); }
+}
+template <int W>
+__device__ __forceinline__ void st_split(__nv_bfloat16* p, long long lo_off, const float (&v)[W]) {
+    float lo[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16(v[i]));
+    stb<W>(p, v);
+    stb<W>(p + lo_off, lo);
+}
+__device__ __forceinline__ float acc_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float acc_tanh(float x) { return fmaf(2.f, acc_sigmoid(2.f * x), -1.f); }
+
+template <int U, int NBT, bool BWD, bool X3>
 __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& c, const Smem& sm, const uint32_t tmem_base, unsigned* gbar,
                                               const int u0, const int tile0, const int warp, const int lane) {
     constexpr int N = BWD ? U : 3 * U;
     constexpr uint32_t kAccCols = NBT * N;
     constexpr int EW = Roles<U, NBT, BWD>::kEpi;
     const int H = P.H, B = P.B, T = P.T;
+    const int HP = X3 ? 2 * H : H;             // pitch of a state row
+    const int G4 = X3 ? 8 * H : 4 * H;         // pitch of a saved-gates / gate-gradient row
     const bool dbg_on = P.dbg != nullptr && blockIdx.x == 0 && lane == 0;
     {
         // ------------------------------- epilogue warps --------------------------------------------
@@ -148,9 +173,14 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                         const float* pj = c.proj + (long long)b * c.proj_ld + u;
                         ldf<UT>(pj, pr); ldf<UT>(pj + H, pz); ldf<UT>(pj + 2 * H, pn);
                     }
-                    uint32_t hw[UT / 2];
-                    ldb_raw<UT>(c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * H + u, hw, false);
-                    unpack<UT>(hw, hreg[bt]);
+                    const __nv_bfloat16* hp0 = c.hsx + ((long long)(c.reverse ? T : 0) * B + b) * HP + u;
+                    if constexpr (X3) {
+                        ld_split<UT>(hp0, H, hreg[bt]);
+                    } else {
+                        uint32_t hw[UT / 2];
+                        ldb_raw<UT>(hp0, hw, false);
+                        unpack<UT>(hw, hreg[bt]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < UT; ++j) { pr[j] += sm.bias[uu + j]; pz[j] += sm.bias[U + uu + j]; }
@@ -170,12 +200,20 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     const bool row_ok = b < B;
                     const long long row_in = (long long)tau * B + b;       // input side is indexed by time
                     // ---- operand that does not depend on the recurrence: fetch before waiting for the MMA
-                    uint32_t ir[UT / 2], iz[UT / 2], in_[UT / 2];
+                    constexpr int IW = X3 ? UT : UT / 2;                   // X3: fp32 inputs, else packed bf16
+                    uint32_t ir[IW], iz[IW], in_[IW];
 #pragma unroll
-                    for (int j = 0; j < UT / 2; ++j) { ir[j] = 0u; iz[j] = 0u; in_[j] = 0u; }
+                    for (int j = 0; j < IW; ++j) { ir[j] = 0u; iz[j] = 0u; in_[j] = 0u; }
                     if (row_ok && has_in) {
-                        const __nv_bfloat16* src = c.emb ? c.emb + (long long)id_next[bt] * 3 * H + u : c.dense + row_in * 3 * H + u;
-                        ldb_raw<UT>(src, ir, false); ldb_raw<UT>(src + H, iz, false); ldb_raw<UT>(src + 2 * H, in_, false);
+                        if constexpr (X3) {
+                            const float* src = c.emb ? reinterpret_cast<const float*>(c.emb) + (long long)id_next[bt] * 3 * H + u
+                                                     : reinterpret_cast<const float*>(c.dense) + row_in * 3 * H + u;
+                            ldf<UT>(src, reinterpret_cast<float(&)[UT]>(ir)); ldf<UT>(src + H, reinterpret_cast<float(&)[UT]>(iz));
+                            ldf<UT>(src + 2 * H, reinterpret_cast<float(&)[UT]>(in_));
+                        } else {
+                            const __nv_bfloat16* src = c.emb ? c.emb + (long long)id_next[bt] * 3 * H + u : c.dense + row_in * 3 * H + u;
+                            ldb_raw<UT>(src, ir, false); ldb_raw<UT>(src + H, iz, false); ldb_raw<UT>(src + 2 * H, in_, false);
+                        }
                         if (c.emb && s + 1 < T) id_next[bt] = c.ids[(long long)tau_n * B + b];
                     }
                     if (stamp) FN_STAMP(s, bt, 6);
@@ -185,36 +223,56 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                     const uint32_t ta = tmem_base + lane_sel + (uint32_t)(bt * N) + uu;
                     const uint32_t tp = ta + kAccCols;
                     float a[UT], p[UT], x[UT], r[UT], z[UT], n[UT], g[UT];
+                    auto input = [&](const uint32_t (&w)[IW]) {
+                        if constexpr (X3) {
+#pragma unroll
+                            for (int j = 0; j < UT; ++j) x[j] = __uint_as_float(w[j]);
+                        } else {
+                            unpack<UT>(w, x);
+                        }
+                    };
                     tmem_ld<UT>(ta, a); tmem_ld<UT>(tp, p);
-                    unpack<UT>(ir, x);
+                    input(ir);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) r[j] = fast_sigmoid(a[j] + p[j] + x[j]);
+                    for (int j = 0; j < UT; ++j) r[j] = X3 ? acc_sigmoid(a[j] + p[j] + x[j]) : fast_sigmoid(a[j] + p[j] + x[j]);
                     tmem_ld<UT>(ta + U, a); tmem_ld<UT>(tp + U, p);
-                    unpack<UT>(iz, x);
+                    input(iz);
 #pragma unroll
-                    for (int j = 0; j < UT; ++j) z[j] = fast_sigmoid(a[j] + p[j] + x[j]);
+                    for (int j = 0; j < UT; ++j) z[j] = X3 ? acc_sigmoid(a[j] + p[j] + x[j]) : fast_sigmoid(a[j] + p[j] + x[j]);
                     tmem_ld<UT>(ta + 2 * U, a); tmem_ld<UT>(tp + 2 * U, p);
                     // accumulator consumed: the tensor core may start the next step of this tile
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&sm.acc_empty[bt]);
-                    unpack<UT>(in_, x);
+                    input(in_);
 #pragma unroll
                     for (int j = 0; j < UT; ++j) {
                         g[j] = a[j] + sm.bias[2 * U + uu + j];
-                        n[j] = fast_tanh(p[j] + x[j] + r[j] * g[j]);
+                        n[j] = X3 ? acc_tanh(p[j] + x[j] + r[j] * g[j]) : fast_tanh(p[j] + x[j] + r[j] * g[j]);
                         hreg[bt][j] = (1.f - z[j]) * n[j] + z[j] * hreg[bt][j];
                     }
-                    if (row_ok) stb<UT>(c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * H + u, hreg[bt]);
+                    if (row_ok) {
+                        __nv_bfloat16* hdst = c.hsx + ((long long)(c.reverse ? tau : tau + 1) * B + b) * HP + u;
+                        if constexpr (X3) st_split<UT>(hdst, H, hreg[bt]);
+                        else stb<UT>(hdst, hreg[bt]);
+                    }
                     if (stamp) FN_STAMP(s, bt, 9);
                     if (s + 1 < T) publish_tile(gbar + tile0 + bt, 1, EW * 32, warp == kEpiWarp0 && lane == 0);   // the next step only needs the state
                     if (stamp) FN_STAMP(s, bt, 10);
                     if (row_ok) {
                         if (c.gates) {                               // off the critical path: after the publish
-                            stb<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), r);
-                            stb<UT>(c.gates + gate_off(tau, b, H + u, B, 4 * H), z);
-                            stb<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, 4 * H), n);
-                            stb<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, 4 * H), g);
+                            if constexpr (X3) {
+                                const long long lo = gate_off(tau, b, 4 * H + u, B, G4) - gate_off(tau, b, u, B, G4);
+                                st_split<UT>(c.gates + gate_off(tau, b, u, B, G4), lo, r);
+                                st_split<UT>(c.gates + gate_off(tau, b, H + u, B, G4), lo, z);
+                                st_split<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, G4), lo, n);
+                                st_split<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, G4), lo, g);
+                            } else {
+                                stb<UT>(c.gates + gate_off(tau, b, u, B, 4 * H), r);
+                                stb<UT>(c.gates + gate_off(tau, b, H + u, B, 4 * H), z);
+                                stb<UT>(c.gates + gate_off(tau, b, 2 * H + u, B, 4 * H), n);
+                                stb<UT>(c.gates + gate_off(tau, b, 3 * H + u, B, 4 * H), g);
+                            }
                         }
                         if (s == T - 1 && c.h_final) {               // caller-chosen offset / pitch: no alignment assumed
                             float* hf = c.h_final + (long long)b * c.h_final_ld + u;
@@ -249,20 +307,31 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                 const int tau = c.reverse ? T - 1 - s : s;
                 const long long row = (long long)tau * B + b;
                 // ---- saved forward values and incoming gradients: fetch (chunk 0) before waiting for the MMA
-                uint32_t wr[CH / 2], wz[CH / 2], wn[CH / 2], wg[CH / 2], wh[CH / 2];
+                // saved values: packed bf16 words, or (X3) fp32 = hi + lo plane, combined while the MMAs of the step run
+                constexpr int SW = X3 ? CH : CH / 2;
+                uint32_t wr[SW], wz[SW], wn[SW], wg[SW], wh[SW];
                 float din[CH];
                 auto fetch = [&](int ch) {
                     const int uc = u0 + uu0 + ch * CH;
 #pragma unroll
-                    for (int j = 0; j < CH / 2; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
+                    for (int j = 0; j < SW; ++j) { wr[j] = 0; wz[j] = 0; wn[j] = 0; wg[j] = 0; wh[j] = 0; }
 #pragma unroll
                     for (int j = 0; j < CH; ++j) din[j] = 0.f;
                     if (row_ok && s >= 0) {
+                        if constexpr (X3) {
+                            const long long lo = 128LL * H;                       // 4H columns further on in the blocked layout
+                            ld_split<CH>(c.gates + gate_off(tau, b, uc, B, G4), lo, reinterpret_cast<float(&)[CH]>(wr));
+                            ld_split<CH>(c.gates + gate_off(tau, b, H + uc, B, G4), lo, reinterpret_cast<float(&)[CH]>(wz));
+                            ld_split<CH>(c.gates + gate_off(tau, b, 2 * H + uc, B, G4), lo, reinterpret_cast<float(&)[CH]>(wn));
+                            ld_split<CH>(c.gates + gate_off(tau, b, 3 * H + uc, B, G4), lo, reinterpret_cast<float(&)[CH]>(wg));
+                            ld_split<CH>(c.hsx + (row + (c.reverse ? B : 0)) * HP + uc, H, reinterpret_cast<float(&)[CH]>(wh));
+                        } else {
                         ldb_raw<CH>(c.gates + gate_off(tau, b, uc, B, 4 * H), wr, false);
                         ldb_raw<CH>(c.gates + gate_off(tau, b, H + uc, B, 4 * H), wz, false);
                         ldb_raw<CH>(c.gates + gate_off(tau, b, 2 * H + uc, B, 4 * H), wn, false);
                         ldb_raw<CH>(c.gates + gate_off(tau, b, 3 * H + uc, B, 4 * H), wg, false);
                         ldb_raw<CH>(c.hsx + (row + (c.reverse ? B : 0)) * H + uc, wh, false);   // the state before step s
+                        }
                         if (c.dhs) {
                             if (c.dhs_f32) ldf<CH>(reinterpret_cast<const float*>(c.dhs) + row * H + uc, din);
                             else {
@@ -309,7 +378,15 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                         continue;
                     }
                     float r[CH], z[CH], n[CH], g[CH], hp[CH], o_r[CH], o_z[CH], o_n[CH];
-                    unpack<CH>(wr, r); unpack<CH>(wz, z); unpack<CH>(wn, n); unpack<CH>(wg, g); unpack<CH>(wh, hp);
+                    if constexpr (X3) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            r[j] = __uint_as_float(wr[j]); z[j] = __uint_as_float(wz[j]); n[j] = __uint_as_float(wn[j]);
+                            g[j] = __uint_as_float(wg[j]); hp[j] = __uint_as_float(wh[j]);
+                        }
+                    } else {
+                        unpack<CH>(wr, r); unpack<CH>(wz, z); unpack<CH>(wn, n); unpack<CH>(wg, g); unpack<CH>(wh, hp);
+                    }
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
                         const float dnp = dh[j] * (1.f - z[j]) * (1.f - n[j] * n[j]);
@@ -320,16 +397,24 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
                         carry[ch * CH + j] = dh[j] * z[j];
                     }
                     if (row_ok) {
-                        __nv_bfloat16* dgp = c.dg + row * 4 * H + uc;
-                        stb<CH>(dgp, o_r); stb<CH>(dgp + H, o_z); stb<CH>(dgp + 3 * H, o_n);
-                        if (NCHK > 1) stb<CH>(dgp + 2 * H, o_i);
+                        __nv_bfloat16* dgp = c.dg + row * G4 + uc;
+                        if constexpr (X3) {
+                            st_split<CH>(dgp, 4 * H, o_r); st_split<CH>(dgp + H, 4 * H, o_z); st_split<CH>(dgp + 3 * H, 4 * H, o_n);
+                            if (NCHK > 1) st_split<CH>(dgp + 2 * H, 4 * H, o_i);
+                        } else {
+                            stb<CH>(dgp, o_r); stb<CH>(dgp + H, o_z); stb<CH>(dgp + 3 * H, o_n);
+                            if (NCHK > 1) stb<CH>(dgp + 2 * H, o_i);
+                        }
                     }
                 }
                 if (s < 0) continue;
                 if (stamp) FN_STAMP(i, bt, 9);
                 publish_tile(gflag, NBT == 2 ? 1 + grp : 1, NBT == 2 ? 128 : EW * 32, (NBT == 2 ? (warp - kEpiWarp0) % 4 == 0 : warp == kEpiWarp0) && lane == 0);   // the recurrence consumes (dr, dz, dn*r) only
                 if (stamp) FN_STAMP(i, bt, 10);
-                if (NCHK == 1 && row_ok) stb<CH>(c.dg + row * 4 * H + u0 + uu0 + 2 * H, o_i);
+                if (NCHK == 1 && row_ok) {
+                    if constexpr (X3) st_split<CH>(c.dg + row * G4 + u0 + uu0 + 2 * H, 4 * H, o_i);
+                    else stb<CH>(c.dg + row * 4 * H + u0 + uu0 + 2 * H, o_i);
+                }
             }
         }
         tc::tc_fence_before();
@@ -340,7 +425,7 @@ __device__ __forceinline__ void epilogue_role(const TcLaunch& P, const TcChain& 
 // U = hidden units per CTA, NBT = 128-row batch tiles per chain.  BWD = false: N = 3U gate columns,
 // K = H.  BWD = true: N = U, K = 3H (A = gate gradients of the following step, pitch 4H).
 // =====================================================================================================
-template <int U, int NBT, bool BWD, int KCH>
+template <int U, int NBT, bool BWD, int KCH, bool X3>
 __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kernel(const __grid_constant__ TcLaunch P) {
     constexpr int EW = Roles<U, NBT, BWD>::kEpi;
     constexpr int N = BWD ? U : 3 * U;
@@ -350,7 +435,7 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
     static_assert(kNeedCols <= 512, "TMEM columns");
     extern __shared__ uint8_t smem_raw[];
     const int H = P.H, B = P.B, T = P.T, S = P.stages;
-    const int K = BWD ? 3 * H : H;
+    const int K = (BWD ? 3 * H : H) * (X3 ? 3 : 1);            // X3: three plane products side by side along K
     const int nkc = K / 64;
     const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
     constexpr uint32_t stage_bytes = KCH * kATile;             // one ring stage: 128 rows x (KCH * 64) K
@@ -439,9 +524,18 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
                             tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
 #pragma unroll
                             for (int q = 0; q < KCH; ++q) {
-                                // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r)
-                                const int cq = col + q * 64;
-                                const int cc = (BWD && cq >= 2 * H) ? cq + H : cq;
+                                // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r).
+                                // X3: K block -> (plane product, column): products 0 / 2 read the hi plane, product 1 the lo
+                                // plane (forward: [B][H hi | H lo]; backward: [B][4H hi | 4H lo]); the weights' K axis is
+                                // laid out [hi | hi | lo] by the caller, so their column is the K index itself.
+                                int cq = col + q * 64, plane = 0;
+                                if constexpr (X3) {
+                                    const int KB = BWD ? 3 * H : H;
+                                    const int prod = cq / KB;
+                                    cq -= prod * KB;
+                                    plane = prod == 1 ? (BWD ? 4 * H : H) : 0;
+                                }
+                                const int cc = ((BWD && cq >= 2 * H) ? cq + H : cq) + plane;
                                 tc::tma_load_3d_u32(sa + q * kATile, &c.tmA, fb, cc, (tile0 + bt) * 128, slab);
                             }
                         }
@@ -554,7 +648,7 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
         }
     };
 
-    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + EW) epilogue_role<U, NBT, BWD>(P, c, sm, tmem_base, gbar, u0, tile0, warp, lane);
+    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + EW) epilogue_role<U, NBT, BWD, X3>(P, c, sm, tmem_base, gbar, u0, tile0, warp, lane);
     else if (warp == 1) mma_role();
     else if (lrank >= 0 && lrank < n_ls) state_loader_role();
     else if (trank >= 0 && trank < n_lw) tail_loader_role();
@@ -569,22 +663,25 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
 long long* g_dbg = nullptr;
 // U for a launch of n_chains chains: the widest slice that fits the grid on the machine -- the streamed state
 // slab is re-read by every slice of a chain, so fewer, wider slices mean less traffic per FLOP and bigger MMAs.
-int pick_u_tc(int n_chains, int H) {
+int pick_u_tc(int n_chains, int H, bool x3) {
     const int sms = fn_num_sms();
     static const int force_u = env_int("FN_GRU_U", 0);
-    for (int U : {32, 16}) {
+    // bf16x3: the epilogues hold twice the saved values (hi + lo planes), 16-unit slices keep them in registers
+    // (c2: 21.3 vs 23.3 ms per train step)
+    const int order[2] = {x3 ? 16 : 32, x3 ? 32 : 16};
+    for (int U : order) {
         if (force_u && U != force_u) continue;
         if (H % U) continue;
-        if (!tc_plan(U, H, false, true).ok || !tc_plan(U, H, true, true).ok) continue;
+        if (!tc_plan(U, H, false, true, x3 ? 3 : 1).ok || !tc_plan(U, H, true, true, x3 ? 3 : 1).ok) continue;
         if ((long long)n_chains * (H / U) > sms) continue;
         return U;
     }
     return 0;
 }
 
-template <int U, int NBT, bool BWD, int KCH>
+template <int U, int NBT, bool BWD, int KCH, bool X3>
 int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
-    const void* fn = (const void*)gru_tc_kernel<U, NBT, BWD, KCH>;
+    const void* fn = (const void*)gru_tc_kernel<U, NBT, BWD, KCH, X3>;
     FN_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -615,21 +712,22 @@ int launch_tc(const TcLaunch& P, size_t smem, cudaStream_t st) {
     FN_CHECK_CUDA(e);
     return FN_OK;
 }
-template <bool BWD, int KCH>
+template <bool BWD, int KCH, bool X3>
 int dispatch_tc2(int U, int nbt, const TcLaunch& P, size_t smem, cudaStream_t st) {
-    if constexpr (BWD) {
-        if (U == 64) return launch_tc<64, 1, BWD, KCH>(P, smem, st);      // tile-split BPTT only (see run_tc)
+    if constexpr (BWD && !X3) {
+        if (U == 64) return launch_tc<64, 1, BWD, KCH, X3>(P, smem, st);      // tile-split BPTT only (see run_tc)
     }
-    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD, KCH>(P, smem, st) : launch_tc<32, 2, BWD, KCH>(P, smem, st);
-    return nbt == 1 ? launch_tc<16, 1, BWD, KCH>(P, smem, st) : launch_tc<16, 2, BWD, KCH>(P, smem, st);
+    if (U == 32) return nbt == 1 ? launch_tc<32, 1, BWD, KCH, X3>(P, smem, st) : launch_tc<32, 2, BWD, KCH, X3>(P, smem, st);
+    return nbt == 1 ? launch_tc<16, 1, BWD, KCH, X3>(P, smem, st) : launch_tc<16, 2, BWD, KCH, X3>(P, smem, st);
 }
-template <bool BWD>
+template <bool BWD, bool X3>
 int dispatch_tc(int U, int nbt, int kch, const TcLaunch& P, size_t smem, cudaStream_t st) {
-    return kch == 4 ? dispatch_tc2<BWD, 4>(U, nbt, P, smem, st)
-         : kch == 2 ? dispatch_tc2<BWD, 2>(U, nbt, P, smem, st) : dispatch_tc2<BWD, 1>(U, nbt, P, smem, st);
+    return kch == 4 ? dispatch_tc2<BWD, 4, X3>(U, nbt, P, smem, st)
+         : kch == 2 ? dispatch_tc2<BWD, 2, X3>(U, nbt, P, smem, st) : dispatch_tc2<BWD, 1, X3>(U, nbt, P, smem, st);
 }
 
-int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
+// x3: bf16x3 mode (see epilogue_role): hi / lo plane operands, three plane products per recurrent product
+int run_tc(bool bwd, bool x3, const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws, size_t ws_bytes,
            cudaStream_t st) {
     FN_REQUIRE(chains && n_chains > 0, "fn_gru_seq_bf16: no chains");
     FN_REQUIRE(B > 0 && T > 0 && H >= 64 && H % 64 == 0, "fn_gru_seq_bf16: need H %% 64 == 0 (H=%d)", H);
@@ -642,7 +740,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
     while (done < n_chains) {
         int group = n_chains - done < kMaxChainsTc ? n_chains - done : kMaxChainsTc, U = 0;
         for (; group >= 1; --group)
-            if ((U = pick_u_tc(group, H)) != 0) break;
+            if ((U = pick_u_tc(group, H, x3)) != 0) break;
         FN_REQUIRE(group >= 1, "fn_gru_seq_bf16: H=%d not supported by the tcgen05 path", H);
         // BPTT, tile split: the product has N = U columns and tcgen05.mma costs >= ~43 cycles whatever N <= 64 (it is
         // bound by the 4 KB A-tile read), so 64-unit slices double the work per MMA; each CTA then takes ONE 128-row
@@ -650,7 +748,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         // kernel) and the CTA count stays n_chains * (H / 32).
         static const int tsplit_env = env_int("FN_GRU_TSPLIT", 1);
         int tsplit = 1, nbt_cta = nbt;
-        if (bwd && tsplit_env && nbt == 2 && H % 64 == 0 && tc_plan(64, H, true, true).ok &&
+        if (bwd && !x3 && tsplit_env && nbt == 2 && H % 64 == 0 && tc_plan(64, H, true, true).ok &&
             (long long)group * (H / 64) * nbt <= fn_num_sms()) {
             U = 64; tsplit = nbt; nbt_cta = 1;
         }
@@ -669,15 +767,18 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
                 FN_REQUIRE(s.w_hh && s.b_hh, "fn_gru_seq_fwd_bf16: chain %d misses weights", done + i);
                 FN_REQUIRE(!s.emb || s.ids, "fn_gru_seq_fwd_bf16: chain %d has emb without ids", done + i);
                 FN_REQUIRE(!(s.emb && s.dense), "fn_gru_seq_fwd_bf16: chain %d has both a token and a dense input", done + i);
-                rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh, 3ull * H, H, H, U, 64);
+                const unsigned long long kw = x3 ? 3ull * H : H, ka = x3 ? 2ull * H : H;   // x3: W [3H][hi|hi|lo], state [hi|lo]
+                rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh, 3ull * H, kw, kw, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, H, H, 128 / cs, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, ka, ka, 128 / cs, 64);
                 if (rc) return rc;
             } else {
                 FN_REQUIRE(s.w_hh_t && s.gates && s.dg && s.dh0, "fn_gru_seq_bwd_bf16: chain %d misses buffers", done + i);
-                rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh_t, H, 3ull * H, 3ull * H, U, 64);
+                const unsigned long long kw = x3 ? 9ull * H : 3ull * H, ka = x3 ? 8ull * H : 4ull * H;
+                FN_REQUIRE(!x3 || !s.dhs || s.dhs_f32, "fn_gru_seq_bwd_bf16x3: dhs must be fp32");
+                rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh_t, H, kw, kw, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, 4ull * H, 4ull * H, 128 / cs, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, ka, ka, 128 / cs, 64);
                 if (rc) return rc;
             }
             d.b_hh = s.b_hh; d.emb = (const __nv_bfloat16*)s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
@@ -690,7 +791,7 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
         P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H; P.tsplit = tsplit;
-        const TcPlan pl = tc_plan(U, H, bwd, true);
+        const TcPlan pl = tc_plan(U, H, bwd, true, x3 ? 3 : 1);
         const int kch = pl.kch;
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
         // Issuing warps per stream.  A ring slot must always be filled by the SAME loader (the "slot free" parity wait
@@ -703,7 +804,8 @@ int run_tc(bool bwd, const FnGruChainBf16* chains, int n_chains, int B, int T, i
         while (P.stages % P.ls) --P.ls;
         while (P.wst > 0 && P.wst % P.lw) --P.lw;
         P.dbg = g_dbg;
-        const int rc = bwd ? dispatch_tc<true>(U, nbt_cta, kch, P, pl.smem, st) : dispatch_tc<false>(U, nbt_cta, kch, P, pl.smem, st);
+        const int rc = x3 ? (bwd ? dispatch_tc<true, true>(U, nbt_cta, kch, P, pl.smem, st) : dispatch_tc<false, true>(U, nbt_cta, kch, P, pl.smem, st))
+                          : (bwd ? dispatch_tc<true, false>(U, nbt_cta, kch, P, pl.smem, st) : dispatch_tc<false, false>(U, nbt_cta, kch, P, pl.smem, st));
         if (rc != FN_OK) return rc;
         done += group;
     }
@@ -724,11 +826,19 @@ extern "C" int fn_gru_seq_fwd_bf16(const FnGruChainBf16* chains, int n_chains, i
                                    size_t barrier_ws_bytes, void* stream) {
     if (fn_gru2_eligible(false, n_chains, B, H))          // two batch tiles: the CTA-pair kernel (fn_gru_tc2.cu)
         return fn_gru2_run(false, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
-    return run_tc(false, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
+    return run_tc(false, false, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
 }
 extern "C" int fn_gru_seq_bwd_bf16(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
                                    size_t barrier_ws_bytes, void* stream) {
     if (fn_gru2_eligible(true, n_chains, B, H))
         return fn_gru2_run(true, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
-    return run_tc(true, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
+    return run_tc(true, false, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int fn_gru_seq_fwd_bf16x3(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                                     size_t barrier_ws_bytes, void* stream) {
+    return run_tc(false, true, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int fn_gru_seq_bwd_bf16x3(const FnGruChainBf16* chains, int n_chains, int B, int T, int H, void* barrier_ws,
+                                     size_t barrier_ws_bytes, void* stream) {
+    return run_tc(true, true, chains, n_chains, B, T, H, barrier_ws, barrier_ws_bytes, (cudaStream_t)stream);
 }

@@ -240,9 +240,10 @@ struct TcPlan {
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
 // slot_per_stage: a weight-ring slot holds the kch chunks of one stage (fn_gru_tc.cu) instead of one chunk (fn_decode_tc.cu).
-TcPlan tc_plan_k(int U, int H, bool bwd, bool slot_per_stage, int kch_req) {
+// kmul: plane products along K (3 in bf16x3 mode, see fn_gru_tc.cu)
+TcPlan tc_plan_k(int U, int H, bool bwd, bool slot_per_stage, int kch_req, int kmul = 1) {
     TcPlan pl{};
-    const int N = bwd ? U : 3 * U, nkc = (bwd ? 3 * H : H) / 64;
+    const int N = bwd ? U : 3 * U, nkc = kmul * (bwd ? 3 * H : H) / 64;
     const long long w_chunk = (long long)N * 128;
     const long long budget = (long long)fn_max_smem_optin() - (long long)kSmemTail;
     // state ring / weight ring when the weights do not all fit.  Defaults from the config-3 sweep (H = 1024, U = 32):
@@ -287,12 +288,12 @@ TcPlan tc_plan_k(int U, int H, bool bwd, bool slot_per_stage, int kch_req) {
     return pl;
 }
 
-TcPlan tc_plan(int U, int H, bool bwd, bool slot_per_stage = false) {
+TcPlan tc_plan(int U, int H, bool bwd, bool slot_per_stage = false, int kmul = 1) {
     static const int kch_f = env_int("FN_GRU_KCH", 4), kch_b = env_int("FN_GRU_KCH_BWD", kch_f);
     int kch = slot_per_stage ? (bwd ? kch_b : kch_f) : 2;
     if (kch != 1 && kch != 2 && kch != 4) kch = 2;
-    TcPlan pl = tc_plan_k(U, H, bwd, slot_per_stage, kch);
-    while (!pl.ok && kch > 1 && slot_per_stage) pl = tc_plan_k(U, H, bwd, slot_per_stage, kch >>= 1);   // smaller stages fit more often
+    TcPlan pl = tc_plan_k(U, H, bwd, slot_per_stage, kch, kmul);
+    while (!pl.ok && kch > 1 && slot_per_stage) pl = tc_plan_k(U, H, bwd, slot_per_stage, kch >>= 1, kmul);   // smaller stages fit more often
     return pl;
 }
 

@@ -29,10 +29,15 @@ struct GemmParams {
     int splits, kb_per_split;      // split-K: grid.z CTAs per output tile, each owning kb_per_split K blocks
     int issue_lanes;               // lanes of the producer warp that issue TMA boxes (1, 2 or 4)
     float* partial;                // [splits][M][N] fp32 partial products (splits > 1), reduced by splitk_reduce_kernel
+    // bf16x3 mode (fn_tc_gemm_bf16x3): an fp32 operand is two bf16 planes (hi, lo) and the K loop runs over `ncombo` plane
+    // products of nkb_base K blocks each -- hi*hi, then lo*hi / hi*lo for every operand that has a lo plane -- into ONE fp32
+    // accumulator.  combo_sel: two bits per product, bit 0 = A's lo plane, bit 1 = B's lo plane.  Plain bf16: 1 product.
+    int ncombo, nkb_base, combo_sel;
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -42,13 +47,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int nkb_total = (p.K + BK - 1) / BK;
+    const int nkb_total = p.nkb_base * p.ncombo;
     const int kb_first = blockIdx.z * p.kb_per_split;
     const int nkb = max(0, min(p.kb_per_split, nkb_total - kb_first));   // K blocks of this split
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
+        if (p.ncombo > 1) { tc::prefetch_tmap(&tmAlo); tc::prefetch_tmap(&tmBlo); }
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(acc_full, 1);
         tc::fence_barrier_init();
@@ -63,7 +69,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // control warps run converged; one elected lane issues (see fn_gru_tc.cu)
         const uint32_t full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty), s0 = tc::smem_u32(smem);
         uint32_t st = 0, ph = 1;
+        int combo = 0, kk = kb_first;                                  // plane product and K block inside it
+        while (p.nkb_base > 0 && kk >= p.nkb_base) { kk -= p.nkb_base; ++combo; }
         for (int kb = 0; kb < nkb; ++kb) {
+            const int sel = (p.combo_sel >> (2 * combo)) & 3;
             tc::mbar_wait_u32(empty0 + st * 8u, ph);                   // slot free (passes immediately on first lap)
             // A stage is 4 boxes of 64 rows x 64 columns (8 KB): lanes 0..3 issue one each.  In tools/ubench_tc.cu one
             // issuing thread completes a TMA op per ~450 cycles whatever the box size while several lanes of one
@@ -73,9 +82,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int op = lane; op < 4; op += p.issue_lanes) {
                 if (lane >= p.issue_lanes) break;
                 const int operand = op >> 1, half = op & 1;
-                const CUtensorMap* tm = operand ? &tmB : &tmA;
+                const CUtensorMap* tm = operand ? ((sel & 2) ? &tmBlo : &tmB) : ((sel & 1) ? &tmAlo : &tmA);
                 const int mn_major = operand ? p.b_mn : p.a_mn;
-                const int r0 = (operand ? n0 : m0) + half * 64, k0 = (kb_first + kb) * BK;
+                const int r0 = (operand ? n0 : m0) + half * 64, k0 = kk * BK;
                 const uint32_t dst = s0 + st * kStageBytes + operand * kTileBytes + half * (kTileBytes / 2);
                 // K-major: box 64(K) x 64(M|N rows), the second half of the tile starts 64 rows * 128 B further on;
                 // MN-major: box 64(M|N) x 64(K), the second 64-wide M|N block starts kTileBytes / 2 further on
@@ -83,6 +92,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             __syncwarp();
             if (++st == kStages) { st = 0; ph ^= 1u; }
+            if (++kk == p.nkb_base) { kk = 0; ++combo; }
         }
         (void)s0;
     } else if (warp == 1) {
@@ -287,30 +297,52 @@ extern "C" int fn_tc_gemm_bf16(const void* A, long long lda, int a_mn_major, con
 extern "C" int fn_tc_gemm_bf16_splitk(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                                       int b_mn_major, void* C, long long ldc, int c_bf16, const float* bias, int M, int N,
                                       int K, int accumulate, int splits, void* workspace, size_t ws_bytes, void* stream) {
+    return fn_tc_gemm_bf16x3(A, lda, 0, a_mn_major, B, ldb, 0, b_mn_major, C, ldc, c_bf16, bias, M, N, K, accumulate, splits,
+                             workspace, ws_bytes, stream);
+}
+
+extern "C" int fn_tc_gemm_bf16x3(const void* A, long long lda, long long a_lo_off, int a_mn_major, const void* B, long long ldb,
+                                 long long b_lo_off, int b_mn_major, void* C, long long ldc, int c_bf16, const float* bias, int M,
+                                 int N, int K, int accumulate, int splits, void* workspace, size_t ws_bytes, void* stream) {
     FN_REQUIRE(A && B && C && M > 0 && N > 0 && K >= 0, "fn_tc_gemm_bf16: bad args");
-    const int nkb_total = (K + BK - 1) / BK;
+    const int nkb_base = (K + BK - 1) / BK;
+    int ncombo = 1, combo_sel = 0;
+    if (a_lo_off) { combo_sel |= 1 << (2 * ncombo); ++ncombo; }
+    if (b_lo_off) { combo_sel |= 2 << (2 * ncombo); ++ncombo; }
+    const int nkb_total = nkb_base * ncombo;
     if (splits < 1) splits = 1;
     if (splits > nkb_total) splits = nkb_total > 0 ? nkb_total : 1;
     FN_REQUIRE(splits == 1 || (workspace && ws_bytes >= fn_tc_gemm_splitk_ws_bytes(M, N, splits)),
                "fn_tc_gemm_bf16_splitk: workspace too small for %d splits", splits);
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmAlo, tmBlo;
     int rc;
     // K-major operand: memory [rows = M|N][cols = K];  MN-major operand: memory [rows = K][cols = M|N]
     rc = a_mn_major ? fn_make_tmap_bf16_2d(&tmA, A, K, M, lda, 64, 64) : fn_make_tmap_bf16_2d(&tmA, A, M, K, lda, 64, 64);
     if (rc) return rc;
     rc = b_mn_major ? fn_make_tmap_bf16_2d(&tmB, B, K, N, ldb, 64, 64) : fn_make_tmap_bf16_2d(&tmB, B, N, K, ldb, 64, 64);
     if (rc) return rc;
+    tmAlo = tmA; tmBlo = tmB;
+    if (a_lo_off) {
+        const void* Al = reinterpret_cast<const __nv_bfloat16*>(A) + a_lo_off;
+        rc = a_mn_major ? fn_make_tmap_bf16_2d(&tmAlo, Al, K, M, lda, 64, 64) : fn_make_tmap_bf16_2d(&tmAlo, Al, M, K, lda, 64, 64);
+        if (rc) return rc;
+    }
+    if (b_lo_off) {
+        const void* Bl = reinterpret_cast<const __nv_bfloat16*>(B) + b_lo_off;
+        rc = b_mn_major ? fn_make_tmap_bf16_2d(&tmBlo, Bl, K, N, ldb, 64, 64) : fn_make_tmap_bf16_2d(&tmBlo, Bl, N, K, ldb, 64, 64);
+        if (rc) return rc;
+    }
     static const int issue_lanes = getenv("FN_GEMM_LANES") ? atoi(getenv("FN_GEMM_LANES")) : 4;
     const int kb_per_split = splits > 1 ? (nkb_total + splits - 1) / splits : (nkb_total > 0 ? nkb_total : 1);
     GemmParams p{C, bias, ldc, M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, c_bf16 ? 1 : 0, accumulate ? 1 : 0,
-                 splits, kb_per_split, issue_lanes, reinterpret_cast<float*>(workspace)};
+                 splits, kb_per_split, issue_lanes, reinterpret_cast<float*>(workspace), ncombo, nkb_base, combo_sel};
     static bool attr_done = false;
     if (!attr_done) {
         FN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done = true;
     }
     dim3 grid(fn_cdiv(N, BN), fn_cdiv(M, BM), splits);
-    tc_gemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+    tc_gemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(tmA, tmB, tmAlo, tmBlo, p);
     FN_LAUNCH_CHECK();
     if (splits > 1) {
         const long long n = (long long)M * N;

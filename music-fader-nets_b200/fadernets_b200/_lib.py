@@ -58,6 +58,11 @@ _SIGNATURES = {
     "fn_gru_seq_ctas_per_chain": (I, [I]),
     "fn_gru_seq_fwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
     "fn_gru_seq_bwd_bf16": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
+    "fn_gru_seq_fwd_bf16x3": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
+    "fn_gru_seq_bwd_bf16x3": (I, [C.POINTER(FnGruChainBf16), I, I, I, I, V, SZ, V]),
+    "fn_tc_gemm_bf16x3": (I, [V, LL, LL, I, V, LL, LL, I, V, LL, I, V, I, I, I, I, I, V, SZ, V]),
+    "fn_split_bf16": (I, [V, LL, LL, V, LL, LL, LL, LL, LL, V]),
+    "fn_time_sum_bf16x3": (I, [V, I, I, I, V, V, V]),
     "fn_gru_debug_timeline": (I, [V]),
     "fn_decode_greedy_ws_bytes": (SZ, [I, I, I, I]),
     "fn_decode_greedy_bf16": (I, [V, V, V, V, V, V, V, V, V, V, V, V, V, I, I, I, I, I, V, V, V, SZ, V]),

@@ -20,8 +20,9 @@ from . import ops
 from ._lib import FaderNetsError, require_cuda
 from .ops import ChainSpec, GruGroupFn, LatentHeadFn, QyXFn, TimeLogSoftmaxFn, VocabLogSoftmaxFn, linear
 from .ops_bf16 import DecoderStackBf16Fn, GruGroupBf16Fn, linear_bf16, GruGroupBf16
+from .ops_x3 import GruGroupX3, linear_x3
 
-PRECISIONS = ("f32", "bf16")
+PRECISIONS = ("f32", "bf16", "bf16x3")
 
 START_TOKEN_FROM_END = 1          # decoder start symbol = one-hot of the LAST vocabulary index (gmm_model.py:120-121)
 CDTL_DIMS = 24                    # chroma conditioning width hard-coded by the reference (gmm_model.py:53)
@@ -116,19 +117,24 @@ class _FaderBase(nn.Module):
     def set_precision(self, precision: str):
         """"f32" (default): every product in fp32 FMA -- the 1e-3 parity mode.  "bf16": the T-scale products
         (GRU gate block, vocabulary / attribute heads, their gradients) on the tcgen05 tensor cores with bf16
-        operands and fp32 accumulation (BASELINE configs 3-5); parameters and reductions stay fp32."""
+        operands and fp32 accumulation (BASELINE configs 3-5); parameters and reductions stay fp32.  "bf16x3": the same
+        tensor-core kernels with every fp32 operand carried as two bf16 planes (hi, lo) and three plane products per
+        product -- fp32-level results (meets the 1e-3 bar of "f32") at tensor-core speed; eval-mode greedy decode runs
+        the exact fp32 path."""
         if precision not in PRECISIONS:
             raise FaderNetsError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
         return self
 
     def _gru(self):
-        return GruGroupBf16 if self.precision == "bf16" else GruGroupFn
+        return GruGroupBf16 if self.precision == "bf16" else GruGroupX3 if self.precision == "bf16x3" else GruGroupFn
 
     def _tlinear(self, x, lin):
         """Linear over a T*B-row activation (time-major hidden states)."""
         if self.precision == "bf16":
             return linear_bf16(x, lin.weight, lin.bias)
+        if self.precision == "bf16x3":
+            return linear_x3(x, lin.weight, lin.bias)
         return linear(x, lin.weight, lin.bias)
 
     # ---------------------------------------------------------------- helpers

@@ -327,12 +327,13 @@ class GruGroupBf16:
     sequences), each run through GruGroupBf16Fn, and the per-sequence outputs are concatenated.  Weight gradients add up
     through autograd.  (The reference's nn.GRU has no batch limit: trainer_gmm.py uses batch_size 128 by default.)"""
     MAX_ROWS = 256
+    FN = GruGroupBf16Fn
 
-    @staticmethod
-    def apply(specs, B, T, H, final_widths, *tensors):
+    @classmethod
+    def apply(cls, specs, B, T, H, final_widths, *tensors):
         import dataclasses
         if B <= GruGroupBf16.MAX_ROWS:
-            return GruGroupBf16Fn.apply(specs, B, T, H, final_widths, *tensors)
+            return cls.FN.apply(specs, B, T, H, final_widths, *tensors)
         outs = []
         for lo in range(0, B, GruGroupBf16.MAX_ROWS):
             hi = min(B, lo + GruGroupBf16.MAX_ROWS)
@@ -346,7 +347,7 @@ class GruGroupBf16:
                     sub_tensors.append(tensors[pos][:, lo:hi].contiguous()); pos += 1
                 if sp.h0 == "tensor":
                     sub_tensors.append(tensors[pos][lo:hi]); pos += 1
-            outs.append(GruGroupBf16Fn.apply(sub_specs, hi - lo, T, H, final_widths, *sub_tensors))
+            outs.append(cls.FN.apply(sub_specs, hi - lo, T, H, final_widths, *sub_tensors))
         nf = len(final_widths)
         return tuple(torch.cat([o[i] for o in outs], 0 if i < nf else 1) for i in range(len(outs[0])))
 

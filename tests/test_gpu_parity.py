@@ -26,14 +26,23 @@ def close(a, b, rtol=RTOL, atol=1e-5, what=""):
     assert err <= lim, f"{what}: max abs err {err:.3e} > {lim:.3e}"
 
 
-def build_model(variant, H, Z, K, weights, dev):
+# Both arithmetic modes that claim the 1e-3 bar: "f32" (fp32 FMA kernels) and "bf16x3" (the tcgen05 kernels with hi / lo
+# bf16 operand planes, three plane products per product).  The tensor-core kernels need H % 64 == 0.
+@pytest.fixture(params=["f32", "bf16x3"])
+def prec(request):
+    return request.param
+
+
+def build_model(variant, H, Z, K, weights, dev, prec="f32"):
     import fadernets_b200 as fn
+    if prec != "f32" and H % 64:
+        pytest.skip("tensor-core path needs H % 64 == 0")
     if variant == "gmvae":
         m = fn.MusicAttrRegGMVAE(342, 3, 16, 24, H, Z, 32, n_component=K)
     else:
         m = fn.MusicAttrRegVAE(342, 3, 16, 24, H, Z, 32)
     m.load_state_dict(weights)           # strict
-    return m.to(dev).train()
+    return m.to(dev).train().set_precision(prec)
 
 
 def fixed_noise(model, *eps):
@@ -50,11 +59,11 @@ def golden_batch(g, dev):
     return d, r, n, c, oh
 
 
-def test_golden_forward_losses_grads(golden, dev):
+def test_golden_forward_losses_grads(golden, dev, prec):
     from fadernets_b200 import trainer, trainer_gmm
     g = golden
     H, Z, K = int(g["H"]), int(g["Z"]), int(g["K"])
-    model = build_model(g["variant"], H, Z, K, g["weights"], dev)
+    model = build_model(g["variant"], H, Z, K, g["weights"], dev, prec)
     d, r, n, c, oh = golden_batch(g, dev)
     # (a) seeded host RNG reproduces the reference's noise draw for draw
     torch.manual_seed(g["seed"] + 3)
@@ -101,12 +110,12 @@ def test_golden_forward_losses_grads(golden, dev):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n_
 
 
-def test_golden_loss_branches(golden, dev):
+def test_golden_loss_branches(golden, dev, prec):
     from fadernets_b200 import trainer_gmm
     g = golden
     if g["variant"] != "gmvae":
         pytest.skip("GM-VAE only")
-    model = build_model("gmvae", int(g["H"]), int(g["Z"]), int(g["K"]), g["weights"], dev)
+    model = build_model("gmvae", int(g["H"]), int(g["Z"]), int(g["K"]), g["weights"], dev, prec)
     trainer_gmm.configure(model, None, {"beta": 0.2})
     d, r, n, c, oh = golden_batch(g, dev)
     for tag, st in (("neg_beta", 5000), ("zero_beta", 10)):
@@ -130,12 +139,12 @@ def test_golden_loss_branches(golden, dev):
         assert np.abs(got - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-6) + 1e-7, k
 
 
-def test_golden_two_train_steps(golden, dev):
+def test_golden_two_train_steps(golden, dev, prec):
     """Two full train() calls from the reference's initial weights: reported scalars and updated weights."""
     import fadernets_b200 as fn
     from fadernets_b200 import trainer, trainer_gmm
     g = golden
-    model = build_model(g["variant"], int(g["H"]), int(g["Z"]), int(g["K"]), g["weights"], dev)
+    model = build_model(g["variant"], int(g["H"]), int(g["Z"]), int(g["K"]), g["weights"], dev, prec)
     opt = fn.FusedAdam(model, lr=1e-3)
     d, r, n, c, oh = golden_batch(g, dev)
     torch.manual_seed(g["seed"] + 4)
@@ -161,9 +170,9 @@ def test_golden_two_train_steps(golden, dev):
         assert np.mean(np.abs(upd - upd_ref) > 2e-5) < 0.01, k
 
 
-def test_golden_greedy_decode(golden, dev):
+def test_golden_greedy_decode(golden, dev, prec):
     g = golden
-    model = build_model(g["variant"], int(g["H"]), int(g["Z"]), int(g["K"]), g["weights"], dev)
+    model = build_model(g["variant"], int(g["H"]), int(g["Z"]), int(g["K"]), g["weights"], dev, prec)
     model.eval()
     zc = torch.cat([torch.from_numpy(g["z_r"]), torch.from_numpy(g["z_n"]), torch.from_numpy(g["c"])], 1).to(dev)
     steps = g["decode/tokens"].shape[1]
@@ -181,17 +190,24 @@ def test_golden_greedy_decode(golden, dev):
 
 @pytest.mark.parametrize("variant,H,Z,K,B,T", [("gmvae", 64, 32, 2, 70, 33), ("vae", 128, 16, 0, 9, 40),
                                                ("gmvae", 256, 128, 2, 16, 24)])
-def test_oracle_train_step(dev, variant, H, Z, K, B, T):
+def test_oracle_train_step(dev, prec, variant, H, Z, K, B, T):
     """One train step vs the CPU oracle at mid sizes (ragged batch, pad tail, K3 chunks not multiple of 64)."""
     import fadernets_b200 as fn
     from fadernets_b200 import trainer, trainer_gmm
     w = fo.init_weights(H, Z, variant, max(K, 1), seed=5)
-    model = build_model(variant, H, Z, K, w, dev)
+    model = build_model(variant, H, Z, K, w, dev, prec)
     opt = fn.FusedAdam(model, lr=1e-3)
     d, r, n, c, rd, nd = fo.synth_batch(B, T, seed=6, pad_tail=True)
     g = torch.Generator().manual_seed(8)
     er, en = torch.randn(B, Z, generator=g), torch.randn(B, Z, generator=g)
-    scal, grads, res = fo.loss_and_grads(w, variant, (d, r, n, c, rd, nd), er, en, 20000, 0.2)
+    scal, grads32, res = fo.loss_and_grads(w, variant, (d, r, n, c, rd, nd), er, en, 20000, 0.2)
+    # Gradients are compared with the SAME restatement evaluated in fp64: the fp32 CPU evaluation is itself 7-8e-4 (of the
+    # tensor's max) away from it on the worst-conditioned tensors of the H = 256 case (mu_n.weight, the reverse encoders'
+    # weight_ih), i.e. it sits at the 1e-3 bar on its own.  Loss values are compared with the fp32 evaluation.
+    w64 = {k: v.double() for k, v in w.items()}
+    _, grads, _ = fo.loss_and_grads(w64, variant, (d, r, n, c.double(), rd, nd), er.double(), en.double(), 20000, 0.2)
+    for k in grads:                       # the two evaluations of the oracle agree to fp32 noise
+        assert float((grads32[k].double() - grads[k]).abs().max()) <= 2e-3 * max(float(grads[k].abs().max()), 1e-6) + 1e-7, k
     fixed_noise(model, er, en)
     dd, rr, nn_, cc = d.to(dev), r.to(dev), n.to(dev), c.to(dev)
     opt.zero_grad()
@@ -207,7 +223,7 @@ def test_oracle_train_step(dev, variant, H, Z, K, B, T):
     bad = []
     params = dict(model.named_parameters())
     for k, ref in grads.items():
-        got = params[k].grad.cpu()
+        got = params[k].grad.cpu().double()
         scale = max(float(ref.abs().max()), 1e-6)
         e = float((got - ref).abs().max())
         if e > RTOL * scale + 1e-7:
