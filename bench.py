@@ -239,6 +239,10 @@ def run_ours(args):
                 e0.record(); rc = orig(name, *a); e1.record()
                 if name == "fn_tc_gemm_bf16":
                     name = f"fn_tc_gemm_bf16 M{a[10]} N{a[11]} K{a[12]} amn{a[2]} bmn{a[5]} cbf{a[8]}"
+                elif name == "fn_tc_gemm_bf16_splitk":
+                    name = f"fn_tc_gemm_bf16_splitk M{a[10]} N{a[11]} K{a[12]} s{a[14]}"
+                elif name == "fn_gemm_f32":
+                    name = f"fn_gemm_f32 M{a[9]} N{a[10]} K{a[11]} sa{a[1]},{a[2]} sb{a[4]},{a[5]}"
                 rec.append((name, e0, e1))
                 return rc
             return orig(name, *a)

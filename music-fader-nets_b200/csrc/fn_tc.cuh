@@ -207,6 +207,21 @@ __device__ __forceinline__ void tma_load_4d_2cta_u32(uint32_t smem_dst, const CU
         ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2cta_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive on the barrier at CTA-relative address `bar` of CTA `cta_rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote_u32(uint32_t bar, uint32_t cta_rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta_rank)
+        : "memory");
+}
 // multicast form: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and the bytes complete on the
 // barrier at `bar`'s CTA-relative offset in the LEADER of each destination CTA's pair
 __device__ __forceinline__ void tma_load_4d_2cta_mc_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,

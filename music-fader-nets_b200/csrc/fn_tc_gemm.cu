@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "fn_tc.cuh"
+#include "fn_tc_gemm_epi.cuh"
 
 namespace {
 
@@ -124,6 +125,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::mbar_wait_warp(acc_full, 0);
         tc::tc_fence_after();
         const int row = m0 + q * 32 + lane;
+        const GemmEpi ep{p.C, p.bias, p.ldc, p.M, p.N, p.c_bf16, p.accumulate, p.splits, p.partial};
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
@@ -135,91 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                if (p.splits > 1) {
-                    float* prow = p.partial + ((long long)blockIdx.z * p.M + row) * p.N + col0;
-                    if (((reinterpret_cast<uintptr_t>(prow) & 15) == 0) && (col0 + 32 <= p.N)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<uint4*>(prow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.N) prow[j] = __uint_as_float(r[j]);
-                    }
-                } else if (p.c_bf16) {
-                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-                    const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= p.N);
-                    if (vec) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
-                            if (p.bias) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(crow + j);
-                            if (p.accumulate) {
-                                const uint4 o = *dst;
-                                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    v[2 * e] += __uint_as_float(ow[e] << 16);
-                                    v[2 * e + 1] += __uint_as_float(ow[e] & 0xffff0000u);
-                                }
-                            }
-                            uint32_t w[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                                w[e] = *reinterpret_cast<const uint32_t*>(&h);
-                            }
-                            *dst = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (col0 + j < p.N) {
-                                float v = __uint_as_float(r[j]);
-                                if (p.bias) v += __ldg(p.bias + col0 + j);
-                                if (p.accumulate) v += __bfloat162float(crow[j]);
-                                crow[j] = __float2bfloat16(v);
-                            }
-                        }
-                    }
-                } else {
-                    float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-                    const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= p.N);
-                    if (vec) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                            if (p.bias) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                            }
-                            if (p.accumulate) {
-                                const float4 o = *reinterpret_cast<const float4*>(crow + j);
-                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                            }
-                            *reinterpret_cast<float4*>(crow + j) = v;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (col0 + j < p.N) {
-                                float v = __uint_as_float(r[j]);
-                                if (p.bias) v += __ldg(p.bias + col0 + j);
-                                if (p.accumulate) v += crow[j];
-                                crow[j] = v;
-                            }
-                        }
-                    }
-                }
+                gemm_store_chunk(ep, blockIdx.z, row, col0, r);
             }
         }
         tc::tc_fence_before();
@@ -251,6 +169,16 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 }  // namespace
+
+void fn_splitk_reduce_launch(const float* partial, int splits, int M, int N, void* C, long long ldc, int c_bf16, const float* bias,
+                             int accumulate, cudaStream_t st) {
+    const long long n = (long long)M * N;
+    splitk_reduce_kernel<<<fn_cdiv(n, 256), 256, 0, st>>>(partial, splits, M, N, C, ldc, c_bf16, bias, accumulate);
+}
+bool fn_tc_gemm2_eligible(int M, int N, int K);
+int fn_tc_gemm2_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmAlo, const CUtensorMap& tmBlo, int a_mn,
+                    int b_mn, void* C, long long ldc, int c_bf16, const float* bias, int M, int N, int K, int accumulate,
+                    int ncombo, int combo_sel, int splits, void* workspace, cudaStream_t st);
 
 // ---- host helpers shared by the tensor-core kernels -------------------------------------------------
 fn_PFN_encodeTiled fn_get_encode_tiled() {
@@ -332,6 +260,9 @@ extern "C" int fn_tc_gemm_bf16x3(const void* A, long long lda, long long a_lo_of
         rc = b_mn_major ? fn_make_tmap_bf16_2d(&tmBlo, Bl, K, N, ldb, 64, 64) : fn_make_tmap_bf16_2d(&tmBlo, Bl, N, K, ldb, 64, 64);
         if (rc) return rc;
     }
+    if (fn_tc_gemm2_eligible(M, N, K))          // large shapes: 256x256 tiles on CTA pairs (fn_tc_gemm2.cu)
+        return fn_tc_gemm2_run(tmA, tmB, tmAlo, tmBlo, a_mn_major, b_mn_major, C, ldc, c_bf16, bias, M, N, K, accumulate, ncombo,
+                               combo_sel, splits, workspace, (cudaStream_t)stream);
     static const int issue_lanes = getenv("FN_GEMM_LANES") ? atoi(getenv("FN_GEMM_LANES")) : 4;
     const int kb_per_split = splits > 1 ? (nkb_total + splits - 1) / splits : (nkb_total > 0 ? nkb_total : 1);
     GemmParams p{C, bias, ldc, M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, c_bf16 ? 1 : 0, accumulate ? 1 : 0,

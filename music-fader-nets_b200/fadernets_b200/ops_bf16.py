@@ -48,15 +48,50 @@ def to_bf16_rows(x: torch.Tensor, cols: int):
 
 
 _SM_SLOTS = 2 * 148          # CTA slots of the 128x128-tile kernel on a B200 (2 per SM)
+_SM_PAIRS = 148 // 2         # CTA pairs of the 256x256-tile kernel (one persistent pair per TPC)
+
+
+def pair_kernel_takes(M: int, N: int, K: int) -> bool:
+    """Mirror of fn_tc_gemm2_eligible (csrc/fn_tc_gemm2.cu): shapes that run on the CTA-pair kernel."""
+    import os
+    if os.environ.get("FN_GEMM_PAIR", "1") == "0":
+        return False
+    return M >= 256 and N >= 384 and ((N + 255) // 256 * 256 - N) * 4 <= N and K >= 64
+
+
+def plan_splits(M: int, N: int, K: int, nprod: int = 1) -> int:
+    """Split-K factor of a tensor-core product with K (x nprod plane products in bf16x3 mode) long and few output tiles (the T*B-row
+    weight gradients).  Pair kernel: work items = splits x 256^2 tiles are dealt round-robin to 74 persistent pairs, so the
+    factor minimises waves x K-loop time + partial-tile traffic; 128^2 kernel: fill the 296 CTA slots once."""
+    pair = pair_kernel_takes(M, N, K)
+    K = K * nprod
+    if K < 8192:
+        return 1
+    if pair:
+        tiles = ((M + 255) // 256) * ((N + 255) // 256)
+        if tiles >= 2 * _SM_PAIRS:
+            return 1
+        # cost model (microseconds): waves x (one tile's K loop / s) at ~21 TFLOP/s per pair + 2 us of pipeline fill per wave,
+        # + s partial tiles written and read back at ~5 TB/s
+        t_tile = 2.0 * 256 * 256 * K / 21.0e6
+        t_part = M * N * 8 / 5.0e6
+        best, best_t = 1, None
+        for s_ in range(1, min(32, K // 1024) + 1):
+            waves = -(-tiles * s_ // _SM_PAIRS)
+            t = waves * (t_tile / s_ + 2.0) + (s_ * t_part if s_ > 1 else 0.0)
+            if best_t is None or t < best_t:
+                best, best_t = s_, t
+        return best
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if tiles >= _SM_SLOTS:
+        return 1
+    return max(1, min(32, _SM_SLOTS // tiles, K // 2048))
 
 
 def tc_gemm(A, a_off, lda, a_mn, B, b_off, ldb, b_mn, Cm, c_off, ldc, bias, M, N, K, accumulate=False):
     """C[M][N] (fp32 or bf16 by Cm.dtype) (+)= A * B (+ bias); operand layouts as in fn_tc_gemm_bf16.
     Products with few output tiles and a long K (the T*B-row weight gradients) are split along K."""
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)
-    splits = 1
-    if K >= 8192 and tiles < _SM_SLOTS:
-        splits = max(1, min(32, _SM_SLOTS // tiles, K // 2048))
+    splits = plan_splits(M, N, K)
     if splits > 1:
         nb = LIB.call("fn_tc_gemm_splitk_ws_bytes", M, N, splits)
         ws = torch.empty(nb, dtype=torch.uint8, device=Cm.device)

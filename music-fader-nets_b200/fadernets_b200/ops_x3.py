@@ -21,7 +21,7 @@ import torch
 
 from ._lib import LIB, FnGruChainBf16, require_cuda, stream_ptr
 from .ops import F32, ChainSpec, _f32c, _p, _st, col_sum, gemm
-from .ops_bf16 import BF16, GruGroupBf16, _pad32, _SM_SLOTS, onehot_bf16, r8
+from .ops_bf16 import BF16, GruGroupBf16, _pad32, onehot_bf16, plan_splits, r8
 
 
 def as_split_grad(g_f32: torch.Tensor) -> torch.Tensor:
@@ -48,11 +48,9 @@ def split_bf16(src: torch.Tensor, rows: int, cols: int, s_r: int, s_c: int, off:
 
 def tc_gemm_x3(A, a_off, lda, a_lo, a_mn, B, b_off, ldb, b_lo, b_mn, Cm, c_off, ldc, bias, M, N, K, accumulate=False):
     """C[M][N] fp32 (+)= A * B (+ bias) over hi / lo planes (a_lo / b_lo: element offset of the lo plane, 0 = exact operand)."""
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)
     nprod = 1 + (1 if a_lo else 0) + (1 if b_lo else 0)
-    splits, nb, ws = 1, 0, None
-    if K * nprod >= 8192 and tiles < _SM_SLOTS:
-        splits = max(1, min(32, _SM_SLOTS // tiles, K * nprod // 2048))
+    nb, ws = 0, None
+    splits = plan_splits(M, N, K, nprod)
     if splits > 1:
         nb = LIB.call("fn_tc_gemm_splitk_ws_bytes", M, N, splits)
         ws = torch.empty(nb, dtype=torch.uint8, device=Cm.device)

@@ -233,7 +233,9 @@ def test_clip_adam_matches_torch(dev):
         close(p, ref[n], rtol=1e-5, atol=1e-7, what=n)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1024), (200, 342, 520), (1000, 72, 136), (64, 8, 8)])
+# (256, 384, 1024) .. (640, 1100, 328) run on the CTA-pair kernel (256x256 tiles; fn_tc_gemm2.cu), the others on 128x128 tiles
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1024), (200, 342, 520), (1000, 72, 136), (64, 8, 8),
+                                   (512, 512, 64), (300, 640, 200), (2100, 1024, 1544), (640, 1100, 328)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("c_bf16", [0, 1])
 def test_tc_gemm_bf16(dev, M, N, K, a_mn, b_mn, c_bf16):
@@ -411,7 +413,15 @@ def test_tc_gemm_splitk(dev, a_mn, b_mn, c_bf16):
     from fadernets_b200._lib import LIB
     from fadernets_b200.ops import _p, _st
     bf = torch.bfloat16
-    M, N, K, splits = 304, 200, 5000, 7        # lda = M, ldb = N in the MN-major layouts: multiples of 8
+    _splitk_case(dev, a_mn, b_mn, c_bf16, 304, 200, 5000, 7)        # 128x128-tile kernel
+    _splitk_case(dev, a_mn, b_mn, c_bf16, 520, 768, 5000, 7)        # CTA-pair kernel (ragged last K split, ragged M)
+    _splitk_case(dev, a_mn, b_mn, c_bf16, 512, 512, 640, 4)         # 10 K blocks over 4 splits: re-planned to non-empty splits
+
+
+def _splitk_case(dev, a_mn, b_mn, c_bf16, M, N, K, splits):
+    from fadernets_b200._lib import LIB
+    from fadernets_b200.ops import _p, _st
+    bf = torch.bfloat16                        # lda = M, ldb = N in the MN-major layouts: multiples of 8
     A = rnd(M, K, seed=1, dev=dev).to(bf); Bm = rnd(K, N, seed=2, dev=dev).to(bf)
     Abuf = A.t().contiguous() if a_mn else A.contiguous()              # a_mn: stored [K][M]
     Bbuf = Bm.contiguous() if b_mn else Bm.t().contiguous()            # b_mn: stored [K][N]; else [N][K]

@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "music-fader-nets_b200")); sys.path.insert
 import torch
 from fadernets_b200._lib import LIB
 from fadernets_b200.ops import _p, _st
+from fadernets_b200.ops_bf16 import plan_splits
 
 dev = torch.device("cuda:0")
 bf = torch.bfloat16
@@ -19,6 +20,7 @@ shapes = [("fwd  x W^T (segment)", TB // 16, 3 * H, H, 0, 0, 1, 1),
           ("dgrad logits dy W_out", TB, H, 342, 0, 1, 1, 1),
           ("square 8192^3      ", 8192, 8192, 8192, 0, 0, 1, 1)]
 for name, M, N, K, a_mn, b_mn, c_bf16, splits in shapes:
+    splits = plan_splits(M, N, K)              # what the train step uses (FN_GEMM_PAIR=0: the 128x128-tile kernel only)
     r8 = lambda x: (x + 7) // 8 * 8
     def padded(rows, cols):                      # TMA row pitch: a multiple of 16 bytes
         buf = torch.zeros(rows, r8(cols), device=dev, dtype=bf)
@@ -52,4 +54,4 @@ for name, M, N, K, a_mn, b_mn, c_bf16, splits in shapes:
     for _ in range(10): torch.matmul(At, Bt)
     e1.record(); torch.cuda.synchronize()
     ms_cb = e0.elapsed_time(e1) / 10
-    print(f"{name} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s  rel.err {err:.2e}   | cuBLAS {ms_cb:.3f} ms {2.0 * M * N * K / ms_cb / 1e9:.0f} TFLOP/s  ratio {ms_cb / ms:.2f}")
+    print(f"{name} M={M} N={N} K={K} splits={splits}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s  rel.err {err:.2e}   | cuBLAS {ms_cb:.3f} ms {2.0 * M * N * K / ms_cb / 1e9:.0f} TFLOP/s  ratio {ms_cb / ms:.2f}")
