@@ -54,6 +54,14 @@ int fn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_op
 int fn_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
                 float* C, long long ldc, const float* bias, int M, int N, int K, int accumulate, void* stream);
 
+/* Split-K variant for products with a long K and few output tiles (latent heads [B x 2H] x [2H x Z], the z-projection
+ * gradients [B x 3H] x [3H x G]): `splits` CTAs per 64x64 tile each reduce a K range into `workspace`
+ * (fn_gemm_f32_splitk_ws_bytes), then a fixed-order reduction applies bias / accumulate -- deterministic. */
+size_t fn_gemm_f32_splitk_ws_bytes(int M, int N, int splits);
+int fn_gemm_f32_splitk(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
+                       float* C, long long ldc, const float* bias, int M, int N, int K, int accumulate, int splits,
+                       void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core GEMM (tcgen05.mma, fp32 accumulation in TMEM, TMA-fed 128B-swizzled smem ring).
  *   C[M][N] (ldc; fp32 or bf16) = (accumulate ? C : 0) + A * B + (bias ? bias[n] : 0)

@@ -137,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                gemm_store_chunk(ep, blockIdx.z, row, col0, r);
+                gemm_store_chunk(ep, blockIdx.z, row, col0, p.N, r);
             }
         }
         tc::tc_fence_before();

@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int BM = 256, BN = 256, BK = 64;
+constexpr int BM = 256, BK = 64;                             // BN: template parameter (256, or 176 for the vocabulary)
 constexpr int kStages = 6;
 constexpr int kTileBytes = 128 * BK * 2;                    // 16 KB: one CTA's share of an operand tile
 constexpr int kStageBytes = 2 * kTileBytes;                 // per CTA
@@ -34,6 +34,9 @@ struct Gemm2Params {
     int tiles_n, tiles, items;                              // items = splits * tiles
 };
 
+// BN = 256, or 176 (each CTA supplies 88 columns of B; its 128-row B tile is loaded whole, the MMA reads the first 88 rows):
+// two 176-column tiles cover the 342-wide vocabulary with 3 % padding instead of 33 %.
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const Gemm2Params p) {
@@ -76,7 +79,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int item = pair; item < p.items; item += npairs) {
             const int z = item / p.tiles, t = item - z * p.tiles;
             const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-            const int r0 = (operand ? tn * BN : tm * BM) + (int)rank * 128;
+            const int r0 = operand ? tn * BN + (int)rank * (BN / 2) : tm * BM + (int)rank * 128;
             const int kb_first = z * p.kb_per_split;
             const int nkb = min(p.kb_per_split, nkb_total - kb_first);
             int combo = 0, kk = kb_first;
@@ -113,7 +116,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t a = it & 1u, use = it >> 1;
                 tc::mbar_wait_u32(acce0 + a * 8u, (use & 1u) ^ 1u);      // both CTAs' epilogues have drained this accumulator
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + a * (uint32_t)BN;
+                const uint32_t d_tmem = tmem_base + a * 256u;
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc::mbar_wait_u32(full0 + st * 8u, ph);
                     tc::tc_fence_after();
@@ -143,13 +146,14 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __syncwarp();
             tc::tc_fence_after();
             const int row = tm * BM + (int)rank * 128 + q * 32 + lane;
+            const int n_lim = min(p.epi.N, (tn + 1) * BN);              // BN = 176: the last chunk of a tile is half valid
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < (BN + 31) / 32; ++c) {
                 uint32_t r[32];
-                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)BN + (uint32_t)(c * 32), r);
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u + (uint32_t)(c * 32), r);
                 tc::tmem_ld_wait();
                 const int col0 = tn * BN + c * 32;
-                if (row < p.epi.M && col0 < p.epi.N) gemm_store_chunk(p.epi, z, row, col0, r);
+                if (row < p.epi.M && col0 < n_lim) gemm_store_chunk(p.epi, z, row, col0, n_lim, r);
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -170,13 +174,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 void fn_splitk_reduce_launch(const float* partial, int splits, int M, int N, void* C, long long ldc, int c_bf16, const float* bias,
                              int accumulate, cudaStream_t st);
 
+// Column-tile width for N: 176 where it pads less than 256 (N in (256, 352]: the 342-wide vocabulary), else 256.
+static int pick_bn(int N) { return (N > 256 && N <= 352) ? 176 : 256; }
+
 // Shapes the pair kernel takes (the others stay with the 128x128 kernel): at least one full 256-row tile and N wide enough
-// that 256-column tiles are mostly full (N = 342, the vocabulary, is better served by three 128-column tiles).
+// that its column tiles are mostly full.
 bool fn_tc_gemm2_eligible(int M, int N, int K) {
     static const int on = getenv("FN_GEMM_PAIR") ? atoi(getenv("FN_GEMM_PAIR")) : 1;
     if (!on) return false;
-    const int waste_n = (N + 255) / 256 * 256 - N;
-    return M >= 256 && N >= 384 && waste_n * 4 <= N && K >= 64;
+    const int bn = pick_bn(N), waste_n = (N + bn - 1) / bn * bn - N;
+    return M >= 256 && N > 256 && waste_n * 4 <= N && K >= 64;
 }
 
 int fn_tc_gemm2_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmAlo, const CUtensorMap& tmBlo, int a_mn,
@@ -192,12 +199,14 @@ int fn_tc_gemm2_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
     p.kb_per_split = kb_per_split;
     p.ncombo = ncombo; p.nkb_base = nkb_base; p.combo_sel = combo_sel;
+    const int BN = pick_bn(N);
     p.tiles_n = fn_cdiv(N, BN);
     p.tiles = fn_cdiv(M, BM) * p.tiles_n;
     p.items = p.tiles * splits;
     static bool attr_done = false;
     if (!attr_done) {
-        FN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        FN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        FN_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<176>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_done = true;
     }
     const int max_pairs = fn_num_sms() / 2;
@@ -213,7 +222,8 @@ int fn_tc_gemm2_run(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    FN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel, tmA, tmB, tmAlo, tmBlo, p));
+    if (BN == 256) FN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<256>, tmA, tmB, tmAlo, tmBlo, p));
+    else FN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<176>, tmA, tmB, tmAlo, tmBlo, p));
     if (splits > 1) fn_splitk_reduce_launch(p.epi.partial, splits, M, N, C, ldc, p.epi.c_bf16, bias, p.epi.accumulate, st);
     FN_LAUNCH_CHECK();
     return FN_OK;

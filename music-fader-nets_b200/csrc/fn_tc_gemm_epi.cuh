@@ -13,22 +13,23 @@ struct GemmEpi {
     float* partial;                // [splits][M][N] fp32 partial products (splits > 1)
 };
 
-// r = the thread's 32 accumulator columns [col0, col0 + 32) of `row` (row < M, col0 < N); z = split-K index
-__device__ __forceinline__ void gemm_store_chunk(const GemmEpi& p, int z, int row, int col0, uint32_t (&r)[32]) {
+// r = the thread's 32 accumulator columns [col0, col0 + 32) of `row` (row < M, col0 < n_lim); columns >= n_lim (<= N: the end of
+// the matrix or of this tile) are not stored; z = split-K index
+__device__ __forceinline__ void gemm_store_chunk(const GemmEpi& p, int z, int row, int col0, int n_lim, uint32_t (&r)[32]) {
     if (p.splits > 1) {
         float* prow = p.partial + ((long long)z * p.M + row) * p.N + col0;
-        if (((reinterpret_cast<uintptr_t>(prow) & 15) == 0) && (col0 + 32 <= p.N)) {
+        if (((reinterpret_cast<uintptr_t>(prow) & 15) == 0) && (col0 + 32 <= n_lim)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<uint4*>(prow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) prow[j] = __uint_as_float(r[j]);
+                if (col0 + j < n_lim) prow[j] = __uint_as_float(r[j]);
         }
     } else if (p.c_bf16) {
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-        const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= p.N);
+        const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= n_lim);
         if (vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -62,7 +63,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpi& p, int z, int ro
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if (col0 + j < p.N) {
+                if (col0 + j < n_lim) {
                     float v = __uint_as_float(r[j]);
                     if (p.bias) v += __ldg(p.bias + col0 + j);
                     if (p.accumulate) v += __bfloat162float(crow[j]);
@@ -72,7 +73,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpi& p, int z, int ro
         }
     } else {
         float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-        const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= p.N);
+        const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (col0 + 32 <= n_lim);
         if (vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -91,7 +92,7 @@ __device__ __forceinline__ void gemm_store_chunk(const GemmEpi& p, int z, int ro
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if (col0 + j < p.N) {
+                if (col0 + j < n_lim) {
                     float v = __uint_as_float(r[j]);
                     if (p.bias) v += __ldg(p.bias + col0 + j);
                     if (p.accumulate) v += crow[j];

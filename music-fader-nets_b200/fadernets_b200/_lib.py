@@ -50,6 +50,8 @@ _SIGNATURES = {
     "fn_source_hash": (C.c_char_p, []),
     "fn_device_info": (I, [C.POINTER(I)] * 4),
     "fn_gemm_f32": (I, [V, LL, LL, V, LL, LL, V, LL, V, I, I, I, I, V]),
+    "fn_gemm_f32_splitk_ws_bytes": (SZ, [I, I, I]),
+    "fn_gemm_f32_splitk": (I, [V, LL, LL, V, LL, LL, V, LL, V, I, I, I, I, I, V, SZ, V]),
     "fn_tc_gemm_bf16": (I, [V, LL, I, V, LL, I, V, LL, I, V, I, I, I, I, V]),
     "fn_tc_gemm_splitk_ws_bytes": (SZ, [I, I, I]),
     "fn_tc_gemm_bf16_splitk": (I, [V, LL, I, V, LL, I, V, LL, I, V, I, I, I, I, I, V, SZ, V]),
@@ -113,7 +115,7 @@ _SIGNATURES = {
     "fn_grad_norm": (I, [V, LL, V, V, SZ, V]),
     "fn_clip_adam": (I, [V, V, V, V, LL, V, F, F, F, F, F, I, V]),
 }
-_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_source_hash", "fn_latent_scratch_bytes", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
+_UNCHECKED = {"fn_last_error", "fn_abi_version", "fn_source_hash", "fn_latent_scratch_bytes", "fn_gru_seq_ctas_per_chain", "fn_emb_grad_scratch_bytes", "fn_tc_gemm_splitk_ws_bytes", "fn_gemm_f32_splitk_ws_bytes", "fn_decode_greedy_ws_bytes",
               "fn_col_sum_scratch_bytes", "fn_reduce_scratch_bytes"}
 
 

@@ -34,6 +34,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def gemm(A, a_off, sam, sak, B, b_off, sbk, sbn, Cm, c_off, ldc, bias, M, N, K, accumulate=False):
+    # few 64x64 output tiles and a long K (latent heads, z-projection gradients): the K loop of a handful of CTAs is a latency
+    # chain -- split it over enough CTAs to fill the machine (deterministic fixed-order reduction of the partials)
+    tiles = ((M + 63) // 64) * ((N + 63) // 64)
+    if K >= 512 and 0 < tiles <= 48:
+        splits = max(1, min(K // 128, 148 // tiles))
+        if splits > 1:
+            nb = LIB.call("fn_gemm_f32_splitk_ws_bytes", M, N, splits)
+            ws = torch.empty(nb, dtype=torch.uint8, device=Cm.device)
+            LIB.call("fn_gemm_f32_splitk", _p(A, a_off), sam, sak, _p(B, b_off), sbk, sbn, _p(Cm, c_off), ldc, _p(bias),
+                     M, N, K, 1 if accumulate else 0, splits, _p(ws), nb, _st(Cm))
+            return
     LIB.call("fn_gemm_f32", _p(A, a_off), sam, sak, _p(B, b_off), sbk, sbn, _p(Cm, c_off), ldc, _p(bias),
              M, N, K, 1 if accumulate else 0, _st(Cm))
 

@@ -56,7 +56,8 @@ def pair_kernel_takes(M: int, N: int, K: int) -> bool:
     import os
     if os.environ.get("FN_GEMM_PAIR", "1") == "0":
         return False
-    return M >= 256 and N >= 384 and ((N + 255) // 256 * 256 - N) * 4 <= N and K >= 64
+    bn = 176 if 256 < N <= 352 else 256           # column-tile width (176: the 342-wide vocabulary)
+    return M >= 256 and N > 256 and ((N + bn - 1) // bn * bn - N) * 4 <= N and K >= 64
 
 
 def plan_splits(M: int, N: int, K: int, nprod: int = 1) -> int:
@@ -68,12 +69,13 @@ def plan_splits(M: int, N: int, K: int, nprod: int = 1) -> int:
     if K < 8192:
         return 1
     if pair:
-        tiles = ((M + 255) // 256) * ((N + 255) // 256)
+        bn = 176 if 256 < N <= 352 else 256
+        tiles = ((M + 255) // 256) * ((N + bn - 1) // bn)
         if tiles >= 2 * _SM_PAIRS:
             return 1
         # cost model (microseconds): waves x (one tile's K loop / s) at ~21 TFLOP/s per pair + 2 us of pipeline fill per wave,
         # + s partial tiles written and read back at ~5 TB/s
-        t_tile = 2.0 * 256 * 256 * K / 21.0e6
+        t_tile = 2.0 * 256 * bn * K / 21.0e6
         t_part = M * N * 8 / 5.0e6
         best, best_t = 1, None
         for s_ in range(1, min(32, K // 1024) + 1):

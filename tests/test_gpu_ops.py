@@ -235,7 +235,7 @@ def test_clip_adam_matches_torch(dev):
 
 # (256, 384, 1024) .. (640, 1100, 328) run on the CTA-pair kernel (256x256 tiles; fn_tc_gemm2.cu), the others on 128x128 tiles
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 1024), (200, 342, 520), (1000, 72, 136), (64, 8, 8),
-                                   (512, 512, 64), (300, 640, 200), (2100, 1024, 1544), (640, 1100, 328)])
+                                   (512, 512, 64), (300, 640, 200), (2100, 1024, 1544), (640, 1100, 328), (700, 342, 520), (256, 352, 200), (1000, 300, 72)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("c_bf16", [0, 1])
 def test_tc_gemm_bf16(dev, M, N, K, a_mn, b_mn, c_bf16):
@@ -415,6 +415,7 @@ def test_tc_gemm_splitk(dev, a_mn, b_mn, c_bf16):
     bf = torch.bfloat16
     _splitk_case(dev, a_mn, b_mn, c_bf16, 304, 200, 5000, 7)        # 128x128-tile kernel
     _splitk_case(dev, a_mn, b_mn, c_bf16, 520, 768, 5000, 7)        # CTA-pair kernel (ragged last K split, ragged M)
+    _splitk_case(dev, a_mn, b_mn, c_bf16, 3072, 344, 9000, 4)       # 176-column pair tiles (vocabulary width)
     _splitk_case(dev, a_mn, b_mn, c_bf16, 512, 512, 640, 4)         # 10 K blocks over 4 splits: re-planned to non-empty splits
 
 
