@@ -20,7 +20,7 @@ from . import ops
 from ._lib import FaderNetsError, require_cuda
 from .ops import ChainSpec, GruGroupFn, LatentHeadFn, QyXFn, TimeLogSoftmaxFn, VocabLogSoftmaxFn, linear
 from .ops_bf16 import DecoderStackBf16Fn, GruGroupBf16Fn, linear_bf16, GruGroupBf16
-from .ops_x3 import GruGroupX3, linear_x3
+from .ops_x3 import DecoderStackX3Fn, GruGroupX3, linear_x3
 
 PRECISIONS = ("f32", "bf16", "bf16x3")
 
@@ -227,11 +227,12 @@ class _FaderBase(nn.Module):
             tensors += [c.weight_ih, c.bias_ih, c.weight_hh, c.bias_hh, zc,
                         linear(zc, self.linear_init_global.weight, self.linear_init_global.bias)]
             names.append("g")
-        if self.precision == "bf16" and names == ["r", "n", "g"] and B <= 256:
+        if self.precision in ("bf16", "bf16x3") and names == ["r", "n", "g"] and B <= 256:
             # the whole decoder stack as one wavefront (cell 2 one time segment behind cell 1 in the same launches)
             c2 = self.grucell_g_2
-            hs_r, hs_n, hs_g2 = DecoderStackBf16Fn.apply(tuple(specs), B, T, H, *tensors, c2.weight_ih, c2.bias_ih,
-                                                         c2.weight_hh, c2.bias_hh)
+            stack = DecoderStackBf16Fn if self.precision == "bf16" else DecoderStackX3Fn
+            hs_r, hs_n, hs_g2 = stack.apply(tuple(specs), B, T, H, *tensors, c2.weight_ih, c2.bias_ih,
+                                            c2.weight_hh, c2.bias_hh)
             return {"r": hs_r, "n": hs_n, "g2": hs_g2}
         hs = dict(zip(names, self._gru().apply(specs, B, T, H, (), *tensors)))
         if "g" in hs:

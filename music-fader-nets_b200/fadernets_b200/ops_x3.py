@@ -100,7 +100,7 @@ def linear_x3(x, w, b):
     return LinearX3Fn.apply(x, w, b)
 
 
-def _finish_chain_grads_x3(sp, d, dg, dh0, B, T, H):
+def _finish_chain_grads_x3(sp, d, dg, dh0, B, T, H, dxin_done=False):
     """ops_bf16._finish_chain_grads over the split gate-gradient stream dg [T][B][8H] (hi planes | lo planes)."""
     dev = dg.device
     st = stream_ptr(dev)
@@ -135,16 +135,17 @@ def _finish_chain_grads_x3(sp, d, dg, dh0, B, T, H):
         c0, Hin = sp.x_cols
         xin = d["xin"]
         wis, ldw, wlo = d["w_ih_s"]
-        dxin = torch.empty((T, B, Hin), dtype=F32, device=dev)
-        tc_gemm_x3(dg, 0, H8, H4, 0, wis, c0, ldw, wlo, 1, dxin, 0, Hin, None, TB, Hin, K3)
-        if sp.h0 == "xin0":
-            LIB.call("fn_add_f32", _p(dxin), _p(dh0), B * Hin, st)     # xin[0] is also this chain's initial state
+        if not dxin_done:                                              # (the wavefront computes it per segment)
+            dxin = torch.empty((T, B, Hin), dtype=F32, device=dev)
+            tc_gemm_x3(dg, 0, H8, H4, 0, wis, c0, ldw, wlo, 1, dxin, 0, Hin, None, TB, Hin, K3)
+            if sp.h0 == "xin0":
+                LIB.call("fn_add_f32", _p(dxin), _p(dh0), B * Hin, st)     # xin[0] is also this chain's initial state
         tc_gemm_x3(dg, 0, H8, H4, 1, xin, 0, 2 * Hin, Hin, 1, dw_ih, c0, In, None, K3, Hin, TB)
     out = [dw_ih, db_ih, dw_hh, db_hh]
     if sp.z_cols is not None:
         out.append(dz_in)
     if sp.x_cols is not None:
-        out.append(as_split_grad(dxin))
+        out.append(None if dxin is None else as_split_grad(dxin))
     if sp.h0 == "tensor":
         out.append(dh0)
     return out
@@ -284,3 +285,144 @@ class GruGroupX3Fn(torch.autograd.Function):
 class GruGroupX3(GruGroupBf16):
     """GruGroupX3Fn for any batch size (chain groups of <= 256 sequences, like ops_bf16.GruGroupBf16)."""
     FN = GruGroupX3Fn
+
+
+class DecoderStackX3Fn(torch.autograd.Function):
+    """ops_bf16.DecoderStackBf16Fn in bf16x3 mode: the four decoder recurrences as a wavefront (cell 2 one time segment behind
+    cell 1 in shared launches).  Same arguments; returns SPLIT (hs_r, hs_n, hs_g2) [T,B,2H]."""
+
+    @staticmethod
+    def forward(ctx, specs, B: int, T: int, H: int, *tensors):
+        from .ops_bf16 import _segments
+        dev = tensors[0].device
+        require_cuda(*tensors)
+        need_grad = any(ctx.needs_input_grad)
+        K3, H2, H8 = 3 * H, 2 * H, 8 * H
+        st = stream_ptr(dev)
+        keep = []
+        for ci, sp in enumerate(specs):
+            w_ih, b_ih, w_hh, b_hh, z_in, h0 = tensors[6 * ci:6 * ci + 6]
+            z_in, h0 = _f32c(z_in), _f32c(h0)
+            In = w_ih.shape[1]
+            c0, Vin = sp.emb_cols
+            zc0, Zin = sp.z_cols
+            d = dict(w_ih=w_ih, w_hh=w_hh, b_hh=b_hh, z_in=z_in, xin=None, spec=sp)
+            d["w_hh_s"] = split_bf16(w_hh, K3, H, H, 1, triple=True)[0]
+            emb = torch.empty((Vin, K3), dtype=F32, device=dev)
+            LIB.call("fn_transpose_f32", _p(w_ih, c0), In, _p(emb), K3, K3, Vin, 0, st)
+            d["emb"] = emb
+            proj = torch.empty((B, K3), dtype=F32, device=dev)
+            gemm(z_in, 0, Zin, 1, w_ih, zc0, 1, In, proj, 0, K3, b_ih, B, K3, Zin)
+            d["proj"] = proj
+            hsx = torch.empty((T + 1, B, H2), dtype=BF16, device=dev)
+            LIB.call("fn_split_bf16", _p(h0), H, 1, _p(hsx), H2, B, H, H, -1, st)
+            d["hsx"] = hsx
+            d["gates"] = torch.empty((T, _pad32(B), H8), dtype=BF16, device=dev) if need_grad else None
+            keep.append(d)
+        w_ih2, b_ih2, w_hh2, b_hh2 = tensors[18:22]
+        g = keep[2]
+        sp2 = ChainSpec(x_cols=(0, H), h0="xin0", want_hs=True)
+        d2 = dict(w_ih=w_ih2, w_hh=w_hh2, b_hh=b_hh2, z_in=None, xin=g["hsx"][1:], spec=sp2)
+        d2["w_hh_s"] = split_bf16(w_hh2, K3, H, H, 1, triple=True)[0]
+        d2["w_ih_s"] = split_bf16(w_ih2, K3, H, H, 1)
+        d2["hsx"] = torch.empty((T + 1, B, H2), dtype=BF16, device=dev)
+        d2["gates"] = torch.empty((T, _pad32(B), H8), dtype=BF16, device=dev) if need_grad else None
+        dense = torch.empty((T, B, K3), dtype=F32, device=dev)
+        keep.append(d2)
+        wis, ldw, wlo = d2["w_ih_s"]
+
+        S = _segments(T)
+        L = T // S
+        bar = torch.empty(64 * 4, dtype=torch.uint8, device=dev)
+        for k in range(S + 1):
+            chains = (FnGruChainBf16 * 4)()
+            n = 0
+            if k < S:
+                t0 = k * L
+                for d in keep[:3]:
+                    ch = chains[n]; n += 1
+                    ch.w_hh, ch.b_hh = d["w_hh_s"].data_ptr(), d["b_hh"].data_ptr()
+                    ch.emb, ch.ids = d["emb"].data_ptr(), d["spec"].ids.data_ptr() + t0 * B * 4
+                    ch.proj, ch.proj_ld = d["proj"].data_ptr(), K3
+                    ch.hsx = d["hsx"].data_ptr() + t0 * B * H2 * 2
+                    if need_grad:
+                        ch.gates = d["gates"].data_ptr() + t0 * _pad32(B) * H8 * 2
+            if k >= 1:
+                t0 = (k - 1) * L
+                # cell 2's input projection for this segment (fp32): dense[t] = hs_g[t] W_ih2^T + b_ih2, hs_g[t] = slab t+1
+                tc_gemm_x3(g["hsx"], (t0 + 1) * B * H2, H2, H, 0, wis, 0, ldw, wlo, 0, dense, t0 * B * K3, K3, b_ih2, L * B, K3, H)
+                if k == 1:
+                    d2["hsx"][0].copy_(g["hsx"][1])                 # hx[1] <- the new hx[0] at step 0 (gmm_model.py:134-135)
+                ch = chains[n]; n += 1
+                ch.w_hh, ch.b_hh = d2["w_hh_s"].data_ptr(), b_hh2.data_ptr()
+                ch.dense = dense.data_ptr() + t0 * B * K3 * 4
+                ch.hsx = d2["hsx"].data_ptr() + t0 * B * H2 * 2
+                if need_grad:
+                    ch.gates = d2["gates"].data_ptr() + t0 * _pad32(B) * H8 * 2
+            LIB.call("fn_gru_seq_fwd_bf16x3", chains, n, B, L, H, _p(bar), bar.numel(), st)
+        for d in keep:
+            d.pop("emb", None); d.pop("proj", None); d.pop("w_hh_s", None)
+        ctx.keep, ctx.dims, ctx.S = keep, (B, T, H), S
+        return keep[0]["hsx"][1:], keep[1]["hsx"][1:], d2["hsx"][1:]
+
+    @staticmethod
+    def backward(ctx, g_r, g_n, g_2):
+        keep, (B, T, H), S = ctx.keep, ctx.dims, ctx.S
+        if keep is None:
+            raise RuntimeError("fadernets_b200: backward through the decoder stack a second time -- its saved states were "
+                               "freed by the first backward (retain_graph is not supported by this Function)")
+        dev = keep[0]["hsx"].device
+        K3, H2, H4, H8 = 3 * H, 2 * H, 4 * H, 8 * H
+        L = T // S
+        st = stream_ptr(dev)
+        dhs = [None if gr is None else from_split_grad(gr) for gr in (g_r, g_n)]
+        dhs += [torch.empty((T, B, H), dtype=F32, device=dev), None if g_2 is None else from_split_grad(g_2)]
+        whts = [split_bf16(d["w_hh"], H, K3, 1, H, triple=True)[0] for d in keep]     # W_hh^T [H][hi | hi | lo]
+        dgs = [torch.empty((T, B, H8), dtype=BF16, device=dev) for _ in keep]
+        dh0 = [[torch.empty((B, H), dtype=F32, device=dev) for _ in range(2)] for _ in keep]
+        last = [None] * 4
+        bar = torch.empty(64 * 4, dtype=torch.uint8, device=dev)
+        d2 = keep[3]
+        wis, ldw, wlo = d2["w_ih_s"]
+
+        def fill(ch, ci, j, flip):
+            d = keep[ci]
+            t0 = j * L
+            ch.w_hh_t = whts[ci].data_ptr()
+            ch.hsx = d["hsx"].data_ptr() + t0 * B * H2 * 2
+            ch.gates = d["gates"].data_ptr() + t0 * _pad32(B) * H8 * 2
+            ch.dg = dgs[ci].data_ptr() + t0 * B * H8 * 2
+            if dhs[ci] is not None:
+                ch.dhs = dhs[ci].data_ptr() + t0 * B * H * 4
+                ch.dhs_f32 = 1
+            if last[ci] is not None:
+                ch.dh_final, ch.dh_final_ld = last[ci].data_ptr(), H
+            out = dh0[ci][flip]
+            ch.dh0 = out.data_ptr()
+            return out
+
+        for k in range(S + 1):
+            chains = (FnGruChainBf16 * 4)()
+            n = 0
+            new_last = list(last)
+            if k < S:
+                new_last[3] = fill(chains[n], 3, S - 1 - k, k & 1); n += 1
+            if k >= 1:
+                for ci in range(3):
+                    new_last[ci] = fill(chains[n], ci, S - k, k & 1); n += 1
+            LIB.call("fn_gru_seq_bwd_bf16x3", chains, n, B, L, H, _p(bar), bar.numel(), st)
+            last = new_last
+            if k < S:
+                # gradient wrt cell 1's states of this segment = cell 2's input gradient: dgi W_ih2 (fp32)
+                j = S - 1 - k
+                t0 = j * L
+                tc_gemm_x3(dgs[3], t0 * B * H8, H8, H4, 0, wis, 0, ldw, wlo, 1, dhs[2], t0 * B * H, H, None, L * B, H, K3)
+                if j == 0:
+                    LIB.call("fn_add_f32", _p(dhs[2]), _p(last[3]), B * H, st)
+
+        out_grads = []
+        for ci in range(3):
+            out_grads += _finish_chain_grads_x3(keep[ci]["spec"], keep[ci], dgs[ci], last[ci], B, T, H)
+        out_grads += _finish_chain_grads_x3(d2["spec"], d2, dgs[3], last[3], B, T, H, dxin_done=True)[:4]
+        ctx.keep = None
+        return (None, None, None, None) + tuple(out_grads)
