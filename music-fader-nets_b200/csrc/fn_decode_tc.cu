@@ -10,6 +10,10 @@
 //   role 1  input 2    gi2_s  = h1_s W_ih2^T + b_ih2                              needs: h1_s
 //   role 2  cell 2     h2_s   = GRU(gi2_s, h2_{s-1}),  h2_{-1} := h1_0            needs: h2_{s-1} (own), gi2_s
 //   role 3  logits     l_s    = h2_s W_out^T + b_out -> per-CTA arg-max partials   needs: h2_s
+// The recurrent products of the two cells (h_{s-1} W_hh) only need the cell's OWN previous state, so their producers wait for
+// nothing else and the tensor cores run them while the rest of the previous token is still in flight; the late operands
+// (the token = arg-max partials for cell 1, gi2_s for cell 2) are awaited by the gate EPILOGUE.  Per token the dependent
+// chain is therefore two products (roles 1 and 3) and two gate epilogues instead of four products.
 // Sequences are independent, so the two 128-row batch tiles of a 256-row batch ping-pong through the roles.
 // The token of step s+1 is reduced from the partials by every cell-1 thread for its own row (first maximum, like
 // torch.max / the reference's _sampling); a small kernel afterwards turns the partials into the token matrix.
@@ -114,8 +118,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) decode_tc_kernel(const __grid_c
                     const int wr = R.wait_role[w], steps_done = s + R.wait_off[w];
                     if (wr >= 0 && steps_done > 0) fn_spin_until(P.bar + wr * 16 + bt, P.per_step[wr] * (unsigned)steps_done);
                 }
-                asm volatile("fence.proxy.async.global;" ::: "memory");
                 const bool first_of_cell2 = (role == 2 && s == 0);
+                if (first_of_cell2) fn_spin_until(P.bar + 0 * 16 + bt, P.per_step[0]);      // its "previous state" is h1_0
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 const CUtensorMap* tm = first_of_cell2 ? &R.tmA0 : &R.tmA;
                 const int slab = first_of_cell2 ? 1 : s + R.a_slab_off;
                 int col = kres * 64;                       // K order: streamed chunks first (see fn_gru_tc.cu)
@@ -271,8 +276,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) decode_tc_kernel(const __grid_c
                 const int b = bt * 128 + q * 32 + lane;
                 const bool row_ok = b < B;
                 const long long row = (long long)s * B + b;
-                tc::mbar_wait_warp(&sm.acc_full[bt], s & 1);        // the producer has seen every dependency of this step
-                tc::tc_fence_after();
+                // ---- late operands of the cells: the token (arg-max partials of step s-1, role 3) / gi2_s (role 1); one lane
+                // polls, the acquire + warp barrier order the other lanes' loads after it
+                if (role == 0 && s > 0) {
+                    if (lane == 0) fn_spin_until(P.bar + 3 * 16 + bt, P.per_step[3] * (unsigned)s);
+                    __syncwarp();
+                } else if (role == 2) {
+                    if (lane == 0) fn_spin_until(P.bar + 1 * 16 + bt, P.per_step[1] * (unsigned)(s + 1));
+                    __syncwarp();
+                }
                 // ---- input-side operand (cells): token-embedding gather (cell 1) / input projection (cell 2)
                 uint32_t ir[kUT / 2], iz[kUT / 2], in_[kUT / 2];
 #pragma unroll
@@ -301,6 +313,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) decode_tc_kernel(const __grid_c
                         unpack<kUT>(hw, hreg[bt]);
                     }
                 }
+                tc::mbar_wait_warp(&sm.acc_full[bt], s & 1);        // the product of this step (issued as soon as its state operand existed)
+                tc::tc_fence_after();
                 const uint32_t ta = tmem_base + lane_sel + (uint32_t)(bt * kN) + uu;
                 const uint32_t tp = ta + kAccCols;
                 float a0[kUT], a1[kUT], a2[kUT], p[kUT], x[kUT];
@@ -451,12 +465,12 @@ extern "C" int fn_decode_greedy_bf16(const void* w_hh1, const float* b_hh1, cons
         P.per_step[i] = (unsigned)nslices[i] * kEpiWarps;
     }
     FN_REQUIRE(cta <= fn_num_sms(), "fn_decode_greedy_bf16: H=%d needs %d CTAs (> %d SMs)", H, cta, fn_num_sms());
-    // cell 1: own previous step + the arg-max partials of the previous step
-    P.r[0].wait_role[0] = 0; P.r[0].wait_off[0] = 0; P.r[0].wait_role[1] = 3; P.r[0].wait_off[1] = 0;
+    // cell 1: own previous step (the arg-max partials of the previous step are awaited by its epilogue)
+    P.r[0].wait_role[0] = 0; P.r[0].wait_off[0] = 0;
     // input projection of cell 2: cell 1 of this step
     P.r[1].wait_role[0] = 0; P.r[1].wait_off[0] = 1;
-    // cell 2: own previous step + its input projection of this step (which implies cell 1 of this step)
-    P.r[2].wait_role[0] = 2; P.r[2].wait_off[0] = 0; P.r[2].wait_role[1] = 1; P.r[2].wait_off[1] = 1;
+    // cell 2: own previous step (its input projection of this step is awaited by its epilogue)
+    P.r[2].wait_role[0] = 2; P.r[2].wait_off[0] = 0;
     // logits: cell 2 of this step
     P.r[3].wait_role[0] = 2; P.r[3].wait_off[0] = 1;
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
