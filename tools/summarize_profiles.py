@@ -72,3 +72,55 @@ if os.path.exists(rep) or os.path.exists(raw):
     d["c3"] = int(traffic)
     json.dump(d, open(tj, "w"))
     print("GRU kernels:", len(rows) - 2, "launches, DRAM traffic per step", round(traffic / 1e9, 2), "GB")
+
+
+# ---- other full captures (`ncu -i ... --page raw --csv` run on the GPU box): one block of key metrics per launch + a
+# duration-weighted tensor-pipe figure -----------------------------------------------------------------------------------
+def summarize_raw(raw_name, out_name, header, keyfn=lambda nm: "all"):
+    raw = os.path.join(G, raw_name)
+    if not os.path.exists(raw):
+        return
+    rows = list(csv.reader(io.StringIO(open(raw).read())))
+    h, units = rows[0], rows[1]
+    keep = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "launch__registers_per_thread",
+            "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size", "launch__cluster_size",
+            "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}
+    tens, seen = {}, {}
+    for r in rows[2:]:
+        nm = r[h.index("Kernel Name")]
+        try:
+            dur = float(r[h.index("gpu__time_duration.sum")]) * tscale.get(units[h.index("gpu__time_duration.sum")], 1.0)
+            tp = float(r[h.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")])
+            a = tens.setdefault(keyfn(nm), [0.0, 0.0, 0]); a[0] += dur * tp; a[1] += dur; a[2] += 1
+        except Exception:
+            pass
+    with open(os.path.join(P, out_name), "w") as f:
+        f.write(header)
+        for kk, (num, den, n) in tens.items():
+            f.write(f"# {kk}: {n} launches, {den / 1e3:.3f} ms, duration-weighted sm__pipe_tensor_cycles_active (pct of peak, elapsed) = {num / max(den, 1e-9):.1f} %\n")
+        for r in rows[2:]:
+            nm = r[h.index("Kernel Name")]
+            key = (nm, r[h.index("launch__grid_size")] if "launch__grid_size" in h else "")
+            seen[key] = seen.get(key, 0) + 1
+            if seen[key] > 3:                      # at most three launches per (kernel, grid) in the tracked summary
+                continue
+            f.write(f"--- {nm[:140]}\n")
+            for k in keep:
+                if k in h: f.write(f"{k:84s} {r[h.index(k)]:>16s} {units[h.index(k)]}\n")
+    print(out_name, {k: (round(v[1] / 1e3, 3), round(v[0] / max(v[1], 1e-9), 1)) for k, v in tens.items()})
+
+
+summarize_raw(f"{tag}_gemm2_c3_raw.csv", f"{tag}_ncu_gemm2_c3_bf16.txt",
+              "# ncu --set full --clock-control none -k regex:tc_gemm2, bench.py --workload c3: the CTA-pair GEMM launches (fn_tc_gemm2.cu) of ONE train step\n"
+              "# (weight gradients dW_hh / dW_ih with split-K, the wavefront's per-segment x W^T / dy W products, logits and its gradients)\n",
+              lambda nm: "tc_gemm2_kernel<176>" if "176" in nm else "tc_gemm2_kernel<256>")
+summarize_raw(f"{tag}_gru_x3_c2_raw.csv", f"{tag}_ncu_gru_x3_c2.txt",
+              "# ncu --set full --clock-control none -k regex:gru_tc_kernel, bench.py --workload c2_x3 (B=64,T=256,H=512, bf16x3 = fp32 parity on the tensor cores):\n"
+              "# the GRU launches of ONE train step (hi/lo bf16 operand planes, three tensor-core products per algorithmic product)\n",
+              lambda nm: "bwd" if __import__("re").search(r"gru_tc_kernel<\s*\d+,\s*\d+,\s*(1|true)", nm) else "fwd")
+summarize_raw(f"{tag}_decode_c5_raw.csv", f"{tag}_ncu_decode_c5.txt",
+              "# ncu --set full --clock-control none -k regex:decode_tc, bench.py --workload c5: ONE greedy-decode launch (256 sequences x 512 steps, H=1024, bf16)\n")
