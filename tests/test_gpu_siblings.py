@@ -103,3 +103,43 @@ def test_sibling_models_match_reference(lib, path):
     lp = m.global_decoder(zt, g["decode/tokens"].shape[1])
     assert np.array_equal(lp.argmax(-1).cpu().numpy(), g["decode/tokens"])
     close(lp, g["decode/logp"], "decode log-probs", atol=1e-4)
+
+
+@pytest.mark.parametrize("kind", ["singlevae", "cvae", "fader"])
+def test_sibling_models_in_bf16x3_mode(lib, kind):
+    """The sibling models on the tensor-core kernels in bf16x3 mode (hi / lo bf16 operand planes: the fp32 bar, 1e-3) against
+    the fp32 mode of the same model (the mode the golden vectors above pin to the reference) at a hidden size the tensor-core
+    kernels take (H = 64): loss terms and every gradient of one step.  CVAE exercises an encoder chain with token gather AND a
+    time-invariant conditioning projection."""
+    import fadernets_b200 as fn
+    from oracle import fader_oracle as fo
+    dev = torch.device("cuda:0")
+    cls = {"singlevae": fn.MusicAttrSingleVAE, "cvae": fn.MusicAttrCVAE, "fader": fn.MusicAttrFaderNets}[kind]
+    B, T, H, Z = 37, 24, 64, 16
+    torch.manual_seed(11)
+    m32 = cls(342, 3, 16, 24, H, Z, 32)
+    w = {k: v.detach().clone() for k, v in m32.state_dict().items()}
+    d, r, n, c, rd, nd = fo.synth_batch(B, T, seed=12, pad_tail=True)
+    results = {}
+    for prec in ("f32", "bf16x3"):
+        m = cls(342, 3, 16, 24, H, Z, 32)
+        m.load_state_dict(w)
+        m = m.to(dev).train().set_precision(prec)
+        tr = _trainer(kind)
+        opt = fn.FusedAdam(m, lr=1e-3)
+        tr.configure(m, opt, {"beta": 0.2, "lr": 1e-3})
+        dd, rr, nn_, cc = d.to(dev), r.to(dev), n.to(dev), c.to(dev)
+        d_oh, r_oh, n_oh = tr.convert_to_one_hot(dd, 342), tr.convert_to_one_hot(rr, 3), tr.convert_to_one_hot(nn_, 16)
+        rd_t, nd_t = torch.from_numpy(rd).float().unsqueeze(-1), torch.from_numpy(nd).float().unsqueeze(-1)
+        opt.zero_grad()
+        torch.manual_seed(13)                                      # same host-RNG draws (noise, dropout masks) in both modes
+        terms = tr._losses(20000, d_oh, dd, cc, rd, nd) if kind == "singlevae" else tr._losses(20000, d_oh, r_oh, n_oh, dd, cc, rd_t, nd_t)
+        terms[0].backward()
+        results[prec] = ([float(t) for t in terms], {k: p.grad.detach().double().cpu() for k, p in m.named_parameters() if p.grad is not None})
+    (t32, g32), (t3, g3) = results["f32"], results["bf16x3"]
+    for a, b in zip(t3, t32):
+        assert abs(a - b) <= RTOL * max(1.0, abs(b)), (t3, t32)
+    assert g32.keys() == g3.keys() and len(g32) >= 20
+    for k in g32:
+        scale = max(float(g32[k].abs().max()), 1e-6)
+        assert float((g3[k] - g32[k]).abs().max()) <= RTOL * scale + 1e-7, (k, float((g3[k] - g32[k]).abs().max()) / scale)
