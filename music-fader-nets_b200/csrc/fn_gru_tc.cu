@@ -97,6 +97,11 @@ struct TcLaunch {
     int tsplit;            // CTAs per (chain, slice): each owns NBT of the chain's 128-row batch tiles (tsplit * NBT tiles)
     int kres, wst;         // resident K chunks of the weight slice; ring slots for the streamed rest (0 = all resident)
     int ls, lw;            // issuing warps of the state stream (1..4) and of the weight-tail stream (1..2)
+    int x3c;               // bf16x3, compact K loop (whole weight slice resident): the state stream carries each plane ONCE
+                           // ([hi | lo], K'' = 2K) and a hi stage is multiplied with the hi AND the lo weight chunks -- a third
+                           // fewer ring stages (the MMA-issuing warp's per-stage cost paces the kernel) and state bytes
+    int box_rows;          // rows of a streamed state box: 128, or 64 / 32 when the chain's only batch tile has no more rows (the
+                           // MMA still reads 128 rows of the slot; rows of one product are independent and the others are never stored)
 };
 #define FN_STAMP(i, bt, k)                                                                       \
     do {                                                                                         \
@@ -435,7 +440,9 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
     static_assert(kNeedCols <= 512, "TMEM columns");
     extern __shared__ uint8_t smem_raw[];
     const int H = P.H, B = P.B, T = P.T, S = P.stages;
-    const int K = (BWD ? 3 * H : H) * (X3 ? 3 : 1);            // X3: three plane products side by side along K
+    const int Kb = BWD ? 3 * H : H;                            // K of one plane product
+    const bool x3c = X3 && P.x3c;
+    const int K = X3 ? (x3c ? 2 * Kb : 3 * Kb) : Kb;           // X3: the plane products side by side along K (compact: the two planes)
     const int nkc = K / 64;
     const int w_chunk_bytes = N * 128;                         // one 64-wide K chunk of the resident operand
     constexpr uint32_t stage_bytes = KCH * kATile;             // one ring stage: 128 rows x (KCH * 64) K
@@ -485,11 +492,13 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
         if (warp == 0 && tc::elect_one()) {
             tc::mbar_arrive_expect_tx(sm.wbar, (uint32_t)(kres * w_chunk_bytes));
             for (int kc = 0; kc < kres; ++kc) {
+                // compact bf16x3: resident chunks = the hi plane, then the lo plane of the caller's [hi | hi | lo] layout
+                const int kcol = (x3c && kc >= Kb / 64) ? 2 * Kb + (kc - Kb / 64) * 64 : kc * 64;
                 if (!BWD) {
                     for (int g = 0; g < 3; ++g)
-                        tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, sm.wbar, kc * 64, g * H + u0);
+                        tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes + g * U * 128, &c.tmW, sm.wbar, kcol, g * H + u0);
                 } else {
-                    tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes, &c.tmW, sm.wbar, kc * 64, u0);
+                    tc::tma_load_2d(sm.W + (size_t)kc * w_chunk_bytes, &c.tmW, sm.wbar, kcol, u0);
                 }
             }
         }
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
                         const bool mine = (turn == lrank);
                         if (mine) tc::mbar_wait_u32(empty0 + st * 8u, ph);
                         if (mine && tc::elect_one()) {
-                            tc::mbar_arrive_expect_tx_u32(fb, stage_bytes);
+                            tc::mbar_arrive_expect_tx_u32(fb, (uint32_t)(KCH * P.box_rows * 128));
 #pragma unroll
                             for (int q = 0; q < KCH; ++q) {
                                 // dg columns are (dr, dz, dn, dn*r): the recurrent product consumes (dr, dz, dn*r).
@@ -600,7 +609,19 @@ __global__ void __launch_bounds__((Roles<U, NBT, BWD>::kThreads), 1) gru_tc_kern
                     tc::tc_fence_after();
                     if (j == 0) FN_STAMP(i, bt, 4);
                     if (tc::elect_one()) {
-                        issue(d_tmem, adesc0 + (uint64_t)(st * a_step), bd, j == 0);
+                        if (X3 && x3c) {
+                            // a hi-plane stage meets the hi and the lo weight chunks of its K range, a lo-plane stage the hi ones
+                            const int kc0 = j * KCH, npl = Kb / 64;
+                            const uint64_t ad = adesc0 + (uint64_t)(st * a_step);
+                            if (kc0 < npl) {
+                                issue(d_tmem, ad, bdesc0 + (uint64_t)(kc0 * b_step), j == 0);
+                                issue(d_tmem, ad, bdesc0 + (uint64_t)((npl + kc0) * b_step), false);
+                            } else {
+                                issue(d_tmem, ad, bdesc0 + (uint64_t)((kc0 - npl) * b_step), false);
+                            }
+                        } else {
+                            issue(d_tmem, adesc0 + (uint64_t)(st * a_step), bd, j == 0);
+                        }
                         tc::umma_commit_u32(empty0 + st * 8u);
                         if (j == nst - 1) tc::umma_commit(&sm.acc_full[bt]);
                     }
@@ -758,6 +779,11 @@ int run_tc(bool bwd, bool x3, const FnGruChainBf16* chains, int n_chains, int B,
         // and 8 CTAs per cluster -- the MMA-issue loop, not L2 reads, paces the kernel -- and removed.)
         const int cs = 1;
         P.cluster = cs;
+        // a chain of <= 64 (<= 32) rows streams half (quarter) boxes: the recurrences of small batches (BASELINE config 2: B = 64)
+        // are bound by the bytes the state stream moves into shared memory
+        static const int small_box = env_int("FN_GRU_SMALL_BOX", 1);
+        const int box_rows = (small_box && nbt == 1) ? (B <= 32 ? 32 : B <= 64 ? 64 : 128) : 128;
+        P.box_rows = box_rows;
         for (int i = 0; i < group; ++i) {
             const FnGruChainBf16& s = chains[done + i];
             TcChain& d = P.c[i];
@@ -770,7 +796,7 @@ int run_tc(bool bwd, bool x3, const FnGruChainBf16* chains, int n_chains, int B,
                 const unsigned long long kw = x3 ? 3ull * H : H, ka = x3 ? 2ull * H : H;   // x3: W [3H][hi|hi|lo], state [hi|lo]
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh, 3ull * H, kw, kw, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, ka, ka, 128 / cs, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.hsx, T + 1, B, ka, ka, box_rows, 64);
                 if (rc) return rc;
             } else {
                 FN_REQUIRE(s.w_hh_t && s.gates && s.dg && s.dh0, "fn_gru_seq_bwd_bf16: chain %d misses buffers", done + i);
@@ -778,7 +804,7 @@ int run_tc(bool bwd, bool x3, const FnGruChainBf16* chains, int n_chains, int B,
                 FN_REQUIRE(!x3 || !s.dhs || s.dhs_f32, "fn_gru_seq_bwd_bf16x3: dhs must be fp32");
                 rc = fn_make_tmap_bf16_2d(&d.tmW, s.w_hh_t, H, kw, kw, U, 64);
                 if (rc) return rc;
-                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, ka, ka, 128 / cs, 64);
+                rc = fn_make_tmap_bf16_3d(&d.tmA, s.dg, T, B, ka, ka, box_rows, 64);
                 if (rc) return rc;
             }
             d.b_hh = s.b_hh; d.emb = (const __nv_bfloat16*)s.emb; d.ids = s.ids; d.proj = s.proj; d.proj_ld = s.proj_ld;
@@ -791,7 +817,12 @@ int run_tc(bool bwd, bool x3, const FnGruChainBf16* chains, int n_chains, int B,
         }
         P.bar = reinterpret_cast<unsigned*>(barrier_ws) + done * 16;
         P.n_chains = group; P.nslices = H / U; P.B = B; P.T = T; P.H = H; P.tsplit = tsplit;
-        const TcPlan pl = tc_plan(U, H, bwd, true, x3 ? 3 : 1);
+        TcPlan pl = tc_plan(U, H, bwd, true, x3 ? 3 : 1);
+        if (x3) {                                            // compact K loop when the two weight planes fit next to a state ring
+            static const int compact = env_int("FN_X3_COMPACT", 1);
+            const TcPlan pc = tc_plan_x3c(U, H, bwd);
+            if (compact && pc.ok) { pl = pc; P.x3c = 1; }
+        }
         const int kch = pl.kch;
         P.stages = pl.stages; P.kres = pl.kres; P.wst = pl.wst;
         // Issuing warps per stream.  A ring slot must always be filled by the SAME loader (the "slot free" parity wait

@@ -297,6 +297,25 @@ TcPlan tc_plan(int U, int H, bool bwd, bool slot_per_stage = false, int kmul = 1
     return pl;
 }
 
+// bf16x3, compact K loop (fn_gru_tc.cu): BOTH planes of the weight slice resident (2 * K/64 chunks), the state ring behind them;
+// a stage must not straddle the planes, so the chunks per stage divide K/64.
+TcPlan tc_plan_x3c(int U, int H, bool bwd) {
+    TcPlan pl{};
+    const int N = bwd ? U : 3 * U, npl = (bwd ? 3 * H : H) / 64;
+    const long long w_chunk = (long long)N * 128, budget = (long long)fn_max_smem_optin() - (long long)kSmemTail;
+    for (int kch = 4; kch >= 1; kch >>= 1) {
+        if (npl % kch) continue;
+        const long long room = budget - 2LL * npl * w_chunk;
+        long long stages = room / ((long long)kch * kATile);
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages < 2) continue;
+        pl.kch = kch; pl.stages = (int)stages; pl.kres = 2 * npl; pl.wst = 0; pl.ok = true;
+        pl.smem = (size_t)(2LL * npl * w_chunk + stages * kch * kATile) + kSmemTail;
+        return pl;
+    }
+    return pl;
+}
+
 int fn_make_tmap_bf16_3d(CUtensorMap* out, const void* base, unsigned long long d2, unsigned long long d1,
                          unsigned long long d0, unsigned long long ld1, unsigned box1, unsigned box0) {
     fn_PFN_encodeTiled enc = fn_get_encode_tiled();
