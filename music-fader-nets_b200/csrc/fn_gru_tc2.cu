@@ -82,15 +82,18 @@ __device__ __forceinline__ void stage16(uint32_t tile, int row, int k16, const f
     sts16(tile + swz(row, k16 + 1), pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
 }
 // Step hand-over between CTAs.  The state tile is written by the ASYNC proxy (TMA store) and read by the async proxy (TMA
-// loads); cp.async.bulk.wait_group 0 returns once the tile's writes are performed in L2 -- the only level the consumers'
-// TMA loads read -- so the counter increment that follows needs neither a cross-proxy fence nor a releasing fence of
-// its own (each measured at ~1.4k cycles on the step's critical path; FN_GRU2_FENCES=1 restores both, for A/B runs).
-// The consumer side keeps its acquire load: it orders the loader's TMA issue after the observation.
+// loads); cp.async.bulk.wait_group 0 returns once the tile's writes are complete for the issuing thread.  The counter increment
+// that follows is a RELEASING red (bit 0 of FN_GRU2_FENCES, the default): with a relaxed increment (an earlier build of this
+// round) about 3 % of fresh processes showed a run-to-run difference in the states of a few sequences during their first steps
+// (tools/determinism_probe.py in a loop of fresh processes; 0 of 130 with the release) -- the tile's writes are not guaranteed
+// to be visible GPU-wide before a relaxed increment is.  The release costs ~1 ms per config-3 step.  The cross-proxy fences on
+// either side (bits 1 and 2, ~1.4 k cycles each on the step's critical path) stay off: the consumers' TMA loads are issued after
+// the acquire load observed the counter, and both the writes and the reads of the tile go through the async proxy and L2.
 #ifndef FN_GRU2_FENCES
-#define FN_GRU2_FENCES 0
+#define FN_GRU2_FENCES 1      /* bit 0: releasing counter increment; bit 1: producer-side proxy fence; bit 2: consumer-side proxy fence */
 #endif
 __device__ __forceinline__ void publish2(unsigned* ctr) {
-#if FN_GRU2_FENCES
+#if FN_GRU2_FENCES & 1
     fn_red_release(ctr, 1u);
 #else
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                 FN_STAMP2(i, k * 32 + 0);
                 if (i > 0) {
                     fn_spin_until(P.bar + (ch0 + k) * 16 + rank, (unsigned)(P.ppc * i));
-#if FN_GRU2_FENCES
+#if FN_GRU2_FENCES & 4
                     asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
                 }
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_fwd_kernel(const __grid_con
                 __syncwarp();
                 FN_STAMP2(s, k * 32 + 9);
                 if (s + 1 < T && tc::elect_one()) {
-#if FN_GRU2_FENCES
+#if FN_GRU2_FENCES & 2
                     asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
                     publish2(P.bar + (ch0 + k) * 16 + rank);
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_bwd_kernel(const __grid_con
         for (int i = 1; i <= T; ++i) {
             const int slab = c.reverse ? i - 1 : T - i;        // the gate gradient of step s+1 (s = T-1-i), by time
             fn_spin_until(gflag, (unsigned)(P.ppc * i));
-#if FN_GRU2_FENCES
+#if FN_GRU2_FENCES & 4
             asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
             int kc = kres;
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(kThreads2, 1) gru2_bwd_kernel(const __grid_con
                 tc::tma_store_4d_u32(&c.tmS, tc::smem_u32(sm.A), u0, b0, 0, tau);
                 tc::bulk_commit_group();
                 tc::bulk_wait_group<0>();
-#if FN_GRU2_FENCES
+#if FN_GRU2_FENCES & 2
                 asm volatile("fence.proxy.async.global;" ::: "memory");
 #endif
                 publish2(gflag);
