@@ -558,3 +558,88 @@ def sibling_loss_and_grads(w: Weights, kind: str, d, c, r_density, n_density, ep
     grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, gs)}
     scal = dict(loss=loss.detach(), **{k: v.detach() for k, v in terms.items()})
     return scal, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in res.items()}
+
+
+# --------------------------------------------------------------------------- #
+# GLSR regulariser: trainer_glsr.py:118-229                     #
+# --------------------------------------------------------------------------- #
+GLSR_STEPS = 100                  # the regulariser decodes 100 teacher-forced steps (trainer_glsr.py:187,189,212,214)
+GLSR_EPS = 1e-2
+PLAYED_NOTES = (2, 90)            # tokens 2..89: MIDI note-on events (trainer_glsr.py:124-126)
+TIME_SHIFTS = (180, 278)          # tokens 180..277: time shifts used as step separators (:132-134)
+
+
+def glsr_note_density(logp: Tensor) -> Tensor:
+    """approx_note_density (trainer_glsr.py:139-141): per sequence, the probability mass on the note-on tokens summed over time.
+    The reference applies softmax to the decoder's log-probabilities (a re-normalisation of exp(logp))."""
+    p = torch.softmax(logp, -1)
+    return p[..., PLAYED_NOTES[0]:PLAYED_NOTES[1]].sum(-1).sum(1)                     # (B,)
+
+
+def glsr_rhythm_density(logp: Tensor) -> Tensor:
+    """approx_rhythm_density (trainer_glsr.py:143-171), vectorised over the batch with the reference's semantics AS WRITTEN:
+    the running note mass `cur` always reads sequence 0 (`played_notes[0][i]`, :154); at a step whose time-shift mass is
+    >= 0.9 a non-zero `cur` is flushed into `total` as 1 (`cur / cur`: value 1, zero gradient) if it exceeds 1e-2, else as
+    itself; what is left after the last separator is dropped; density = total / (time-shift mass summed over time), and a
+    density of exactly 0 is replaced by a constant."""
+    p = torch.softmax(logp, -1)
+    notes0 = p[0, :, PLAYED_NOTES[0]:PLAYED_NOTES[1]].sum(-1)                         # (S,)  sequence 0, whatever the row
+    seps = p[..., TIME_SHIFTS[0]:TIME_SHIFTS[1]].sum(-1)                              # (B,S)
+    B, S = seps.shape
+    cur = torch.zeros(B, dtype=logp.dtype)
+    total = torch.zeros(B, dtype=logp.dtype)
+    for i in range(S):
+        is_sep = seps[:, i].detach() >= 0.9
+        cur = torch.where(is_sep, cur, cur + notes0[i])
+        flush = is_sep & (cur.detach() != 0)
+        piece = torch.where(cur.detach() > 1e-2, torch.ones_like(cur), cur)
+        total = total + torch.where(flush, piece, torch.zeros_like(cur))
+        cur = torch.where(flush, torch.zeros_like(cur), cur)
+    dens = total / seps.sum(1)
+    return torch.where(total.detach() != 0, dens, torch.zeros_like(dens))
+
+
+def glsr_regulariser(w: Weights, z_r: Tensor, z_n: Tensor, c: Tensor, teacher_ids: Tensor, deltas_r: Tensor, deltas_n: Tensor):
+    """latent_regularized_loss_function of trainer_glsr.py:118-229 (Hadjeres et al.'s GLSR as the reference implements it):
+    finite differences of the two approximated attributes along latent dimension 0, through FOUR extra teacher-forced decodes
+    of 100 steps, pushed towards a standard normal: l = mean(-log N(g; 0, 1)), g = (a(z+) - a(z-)) / (2 delta)."""
+    def fd(attr, zs_plus, zs_minus, deltas):
+        a_p = attr(global_decoder(w, torch.cat(zs_plus + [c], 1), GLSR_STEPS, teacher_ids[:, :GLSR_STEPS])[0])
+        a_m = attr(global_decoder(w, torch.cat(zs_minus + [c], 1), GLSR_STEPS, teacher_ids[:, :GLSR_STEPS])[0])
+        g = (a_p - a_m) / (2 * deltas)
+        return (0.5 * g * g + 0.5 * math.log(2 * math.pi)).mean()
+
+    def shifted(z, d):
+        zz = z.clone()
+        zz[:, 0] = zz[:, 0] + d
+        return zz
+    l_r = fd(glsr_rhythm_density, [shifted(z_r, deltas_r), z_n], [shifted(z_r, -deltas_r), z_n], deltas_r)
+    l_n = fd(glsr_note_density, [z_r, shifted(z_n, deltas_n)], [z_r, shifted(z_n, -deltas_n)], deltas_n)
+    return l_r, l_n
+
+
+def draw_glsr_deltas(B: int):
+    """The CPU-generator draws of one regulariser call, in the reference's order: deltas for z_r, the coin flips of its two
+    decodes, deltas for z_n, the coin flips of its two decodes (trainer_glsr.py:179,187,189,204,212,214; model_v2.py:136)."""
+    d_r = (1 + torch.rand(B)) * GLSR_EPS
+    torch.rand(GLSR_STEPS); torch.rand(GLSR_STEPS)
+    d_n = (1 + torch.rand(B)) * GLSR_EPS
+    torch.rand(GLSR_STEPS); torch.rand(GLSR_STEPS)
+    return d_r, d_n
+
+
+def glsr_loss_and_grads(w: Weights, batch, eps_r, eps_n, deltas_r, deltas_n, step: int, beta: float):
+    """Forward + loss_function + GLSR regulariser + gradients of reference trainer_glsr.py:232-258 (vanilla VAE)."""
+    d, r, n, c, _, _ = batch
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in w.items() if is_live(k)}
+    ww = {**w, **leaves}
+    res = forward(ww, "vae", d, r, n, c, eps_r, eps_n, True)
+    terms = loss_vae(res, d, r, n, step, beta)
+    l_r, l_n = glsr_regulariser(ww, res["z_r"], res["z_n"], c, d, deltas_r, deltas_n) if step > 20 else (torch.zeros(()), torch.zeros(()))
+    loss = terms[0] + l_r + l_n
+    names = list(leaves)
+    gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, gs)}
+    scalars = dict(loss=loss.detach(), CE_X=terms[1].detach(), CE_R=terms[2].detach(), CE_N=terms[3].detach(),
+                   l_r=l_r.detach(), l_n=l_n.detach())
+    return scalars, grads

@@ -286,8 +286,76 @@ def make_sibling_case(kind: str, H: int, Z: int, B: int, T: int, seed: int):
     return g
 
 
+def make_glsr_case(H: int, Z: int, B: int, T: int, seed: int):
+    """GLSR trainer (trainer_glsr.py:82-258) on the unmodified MusicAttrRegVAE: one forward + loss_function + the GLSR
+    regulariser (four extra 100-step decodes) + gradients, and two full train() calls; every CPU-generator draw replayable
+    from the seeds (model noise, coin flips, finite-difference deltas)."""
+    from oracle import fader_oracle as fo
+    gmm_model, model_v2 = load_reference()
+    torch.manual_seed(seed)
+    model = model_v2.MusicAttrRegVAE(342, 3, 16, 24, H, Z, 32)
+    # with default-initialised weights the time-shift mass never reaches the 0.9 separator threshold (and is almost constant over
+    # time), so the rhythm branch of the regulariser is a constant; scaling the time-shift rows of the output projection and
+    # biasing them puts the mass AROUND the threshold with step-to-step variation: separators and accumulation steps alternate
+    # and both branches of approx_rhythm_density run
+    with torch.no_grad():
+        model.linear_out_g.weight[180:278] *= 8.0
+        model.linear_out_g.bias[180:278] += 1.8
+    model.train()
+    args = dict(lr=1e-3, beta=0.2)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args["lr"])
+    ns = extract_step_functions("trainer_glsr.py", trainer_namespace(model, optimizer, args))
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    d, r, n, c, r_density, n_density = fo.synth_batch(B, T, seed=seed + 1, pad_tail=True)
+    d_oh, r_oh, n_oh = (ns["convert_to_one_hot"](x, dims) for x, dims in ((d, 342), (r, 3), (n, 16)))
+    g = {"B": B, "T": T, "H": H, "Z": Z, "d": d.numpy(), "r": r.numpy(), "n": n.numpy(), "c": c.numpy(),
+         "r_density": r_density, "n_density": n_density}
+    for k, v in sd0.items():
+        g["w/" + k] = v.numpy()
+    STEP = 20000
+    torch.manual_seed(seed + 3)
+    optimizer.zero_grad()
+    output, dis, z_out = model(d_oh, r_oh, n_oh, c)
+    out, r_out, n_out = output
+    terms = ns["loss_function"](out, d, r_out, r, n_out, n, dis, STEP, beta=0.2)
+    l_r, l_n = ns["latent_regularized_loss_function"](z_out, r_density, n_density, c)
+    total = terms[0] + l_r + l_n
+    total.backward()
+    for nm, t in zip(("loss", "CE_X", "CE_R", "CE_N"), terms):
+        g["loss/" + nm] = np.float64(t.detach().reshape(-1)[0].item())
+    g["loss/l_r"], g["loss/l_n"] = np.float64(l_r.item()), np.float64(l_n.item())
+    g["loss/total"] = np.float64(total.detach().reshape(-1)[0].item())
+    g["z_r"], g["z_n"] = z_out[0].detach().numpy(), z_out[1].detach().numpy()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            g["grad/" + k] = p.grad.detach().clone().numpy()
+    g["live"] = np.array(sorted(k for k, p in model.named_parameters() if p.grad is not None))
+    # two full train() calls from the initial weights (step > 20: the regulariser is active)
+    model.load_state_dict(sd0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=args["lr"])
+    ns["optimizer"] = optimizer
+    torch.manual_seed(seed + 4)
+    traj, step = [], STEP
+    for it in range(2):
+        step, o = ns["train"](step, d_oh, r_oh, n_oh, d, r, n, c, r_density, n_density)
+        traj.append(o)
+    g["train/outputs"] = np.array(traj, dtype=np.float64)
+    for k, p in model.named_parameters():
+        if ("grad/" + k) in g:
+            g["w2/" + k] = p.detach().clone().numpy()
+    # the regulariser is skipped for step <= 20 (trainer_glsr.py:250-252)
+    model.load_state_dict(sd0)
+    torch.manual_seed(seed + 5)
+    g["eval_early/outputs"] = np.array(ns["evaluate"](10, d_oh, r_oh, n_oh, d, r, n, c, r_density, n_density), dtype=np.float64)
+    return g
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    g = make_glsr_case(16, 8, 3, 104, 81)
+    path = os.path.join(OUT, "glsr_vae_H16_Z8_B3_T104.npz")
+    np.savez_compressed(path, **g)
+    print(path, f"{os.path.getsize(path) / 1e6:.2f} MB", {k: float(v) for k, v in g.items() if k.startswith("loss/")})
     for kind, H, Z, B, T, seed in (("singlevae", 16, 8, 3, 10, 40), ("cvae", 16, 8, 3, 10, 50), ("fader", 16, 8, 4, 9, 60)):
         g = make_sibling_case(kind, H, Z, B, T, seed)
         path = os.path.join(OUT, f"sib_{kind}_H{H}_Z{Z}_B{B}_T{T}.npz")
