@@ -12,7 +12,7 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_FILES = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("sib_"))
+GOLDEN_FILES = sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith(("sib_", "glsr_")))   # glsr_*: tests/test_oracle_glsr.py
 SIBLING_GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "sib_*.npz")))     # sibling models (oracle/gen_golden.py make_sibling_case)
 GOLDEN_SEEDS = {"gmvae_H16_Z8_B3_T12": 10, "vae_H16_Z8_B4_T10": 20, "gmvae_H32_Z16_B2_T9": 30, "gmvae_H64_Z8_B3_T10": 70}   # oracle/gen_golden.py main()
 
