@@ -33,7 +33,7 @@ extern "C" {
 #define FN_ERR_CUDA (-2)     /* a CUDA runtime call failed        */
 #define FN_ERR_UNSUPPORTED (-3)
 
-#define FN_ABI_VERSION 2
+#define FN_ABI_VERSION 3      /* 3: + bf16x3 entry points (fn_gru_seq_*_bf16x3, fn_tc_gemm_bf16x3, fn_split_bf16, fn_time_sum_bf16x3), fn_gemm_f32_splitk; additive */
 
 const char* fn_last_error(void);
 int fn_abi_version(void);

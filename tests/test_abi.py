@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.call("fn_abi_version") == 2
+    assert lib.call("fn_abi_version") == 3
     assert isinstance(lib.dll.fn_last_error(), bytes)
 
 
